@@ -1,0 +1,195 @@
+"""Seeded synthetic weights with the reference's exact state_dict key names.
+
+There are no pretrained checkpoints offline, so parity
+and bench runs use random-init weights.  The generators here emit tensors
+under the *reference's* key names and shapes (waifu2x/models/cunet.py:10-163,
+waifu2x/models/swin_unet.py:119-199, torchvision swin_transformer.py:234-312)
+so the same dict loads into the real reference modules with
+``load_state_dict(strict=True)`` (done in oracle/gen_golden.py) and into the
+B200 engine's weight packer.
+
+Gains are chosen so activations stay O(1) through the stack and the final
+output spans [0, 1] (the clamps and the seam blend are then exercised).
+"""
+import math
+import torch
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def _normal(g, shape, std):
+    return torch.randn(shape, generator=g, dtype=torch.float32) * std
+
+
+def _conv(sd, g, name, cout, cin, kh, kw, gain=1.0, bias_std=0.02, transpose=False):
+    fan_in = cin * kh * kw
+    std = gain * math.sqrt(2.0 / fan_in)
+    shape = (cin, cout, kh, kw) if transpose else (cout, cin, kh, kw)
+    sd[name + ".weight"] = _normal(g, shape, std)
+    sd[name + ".bias"] = _normal(g, (cout,), bias_std)
+
+
+def _linear(sd, g, name, cout, cin, gain=1.0, bias_std=0.02):
+    std = gain * math.sqrt(1.0 / cin)
+    sd[name + ".weight"] = _normal(g, (cout, cin), std)
+    sd[name + ".bias"] = _normal(g, (cout,), bias_std)
+
+
+# ----------------------------------------------------------------------------
+# CUNet family (waifu2x/models/cunet.py)
+# ----------------------------------------------------------------------------
+
+def _unet_conv(sd, g, prefix, cin, cmid, cout, se):
+    _conv(sd, g, prefix + ".conv.0", cmid, cin, 3, 3)
+    _conv(sd, g, prefix + ".conv.2", cout, cmid, 3, 3)
+    if se:
+        _conv(sd, g, prefix + ".seblock.conv1", cout // 8, cout, 1, 1, gain=0.7, bias_std=0.1)
+        _conv(sd, g, prefix + ".seblock.conv2", cout, cout // 8, 1, 1, gain=0.7, bias_std=0.1)
+
+
+def _unet1(sd, g, prefix, cin, cout, deconv):
+    _unet_conv(sd, g, prefix + ".conv1", cin, 32, 64, se=False)
+    _conv(sd, g, prefix + ".conv1_down", 64, 64, 2, 2)
+    _unet_conv(sd, g, prefix + ".conv2", 64, 128, 64, se=True)
+    # ConvTranspose2d(64, 64, 2, 2): weight is (in, out, 2, 2); fan-in per output = 64
+    sd[prefix + ".conv2_up.weight"] = _normal(g, (64, 64, 2, 2), math.sqrt(2.0 / 64))
+    sd[prefix + ".conv2_up.bias"] = _normal(g, (64,), 0.02)
+    _conv(sd, g, prefix + ".conv3", 64, 64, 3, 3, gain=0.7)
+    if deconv:
+        # ConvTranspose2d(64, cout, 4, 2, 3): each output sees 2x2 taps x 64 ch
+        sd[prefix + ".conv_bottom.weight"] = _normal(g, (64, cout, 4, 4), 0.6 * math.sqrt(1.0 / 256))
+        sd[prefix + ".conv_bottom.bias"] = torch.full((cout,), 0.5) + _normal(g, (cout,), 0.02)
+    else:
+        _conv(sd, g, prefix + ".conv_bottom", cout, 64, 3, 3, gain=0.6)
+        sd[prefix + ".conv_bottom.bias"] = torch.full((cout,), 0.5) + _normal(g, (cout,), 0.02)
+
+
+def _unet2(sd, g, prefix, cin, cout):
+    _unet_conv(sd, g, prefix + ".conv1", cin, 32, 64, se=False)
+    _conv(sd, g, prefix + ".conv1_down", 64, 64, 2, 2)
+    _unet_conv(sd, g, prefix + ".conv2", 64, 64, 128, se=True)
+    _conv(sd, g, prefix + ".conv2_down", 128, 128, 2, 2)
+    _unet_conv(sd, g, prefix + ".conv3", 128, 256, 128, se=True)
+    sd[prefix + ".conv3_up.weight"] = _normal(g, (128, 128, 2, 2), math.sqrt(2.0 / 128))
+    sd[prefix + ".conv3_up.bias"] = _normal(g, (128,), 0.02)
+    _unet_conv(sd, g, prefix + ".conv4", 128, 64, 64, se=True)
+    sd[prefix + ".conv4_up.weight"] = _normal(g, (64, 64, 2, 2), math.sqrt(2.0 / 64))
+    sd[prefix + ".conv4_up.bias"] = _normal(g, (64,), 0.02)
+    _conv(sd, g, prefix + ".conv5", 64, 64, 3, 3, gain=0.7)
+    _conv(sd, g, prefix + ".conv_bottom", cout, 64, 3, 3, gain=0.3)
+    sd[prefix + ".conv_bottom.bias"] = _normal(g, (cout,), 0.02)
+
+
+def upcunet_state_dict(seed=0, in_channels=3, out_channels=3):
+    """Keys of ``waifu2x.upcunet`` (cunet.py:139-147)."""
+    g = _gen(seed)
+    sd = {}
+    _unet1(sd, g, "unet1", in_channels, out_channels, deconv=True)
+    _unet2(sd, g, "unet2", in_channels, out_channels)
+    return sd
+
+
+def cunet_state_dict(seed=0, in_channels=3, out_channels=3):
+    """Keys of ``waifu2x.cunet`` (cunet.py:173-181)."""
+    g = _gen(seed)
+    sd = {}
+    _unet1(sd, g, "unet1", in_channels, out_channels, deconv=False)
+    _unet2(sd, g, "unet2", in_channels, out_channels)
+    return sd
+
+
+# ----------------------------------------------------------------------------
+# SwinUNet family (waifu2x/models/swin_unet.py)
+# ----------------------------------------------------------------------------
+
+def relative_position_index(ws=6):
+    """torchvision swin_transformer.py:267-279 (define_relative_position_index)."""
+    coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij"))
+    cf = torch.flatten(coords, 1)
+    rel = (cf[:, :, None] - cf[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1).flatten()
+
+
+def _swin_blocks(sd, g, prefix, dim, heads, layers, ws=6):
+    for i in range(layers):
+        p = f"{prefix}.block.{i}"
+        sd[p + ".attn.relative_position_bias_table"] = _normal(g, ((2 * ws - 1) ** 2, heads), 0.5)
+        sd[p + ".attn.relative_position_index"] = relative_position_index(ws)
+        _linear(sd, g, p + ".attn.qkv", dim * 3, dim, gain=1.0)
+        _linear(sd, g, p + ".attn.proj", dim, dim, gain=0.5)
+        _linear(sd, g, p + ".mlp.0", dim * 2, dim, gain=1.0)
+        _linear(sd, g, p + ".mlp.3", dim, dim * 2, gain=0.5)
+
+
+def swin_unet_state_dict(seed=0, scale_factor=4, in_channels=3, out_channels=3, base_dim=96):
+    """Keys of ``SwinUNetBase`` under the ``unet.`` prefix (swin_unet.py:119-199)."""
+    assert scale_factor in (1, 2, 4)
+    g = _gen(seed)
+    sd = {}
+    C = base_dim
+    H = C // 16
+    _conv(sd, g, "unet.patch.0", C // 2, in_channels, 3, 3)
+    _conv(sd, g, "unet.patch.2", C, C // 2, 3, 3)
+    _swin_blocks(sd, g, "unet.swin1", C, H, 2)
+    _conv(sd, g, "unet.down1.conv", C * 2, C, 2, 2, gain=0.7)
+    _swin_blocks(sd, g, "unet.swin2", C * 2, H, 2)
+    _conv(sd, g, "unet.down2.conv", C * 2, C * 2, 2, 2, gain=0.7)
+    _swin_blocks(sd, g, "unet.swin3", C * 2, H, 6)
+    _linear(sd, g, "unet.up2.proj", C * 2 * 4, C * 2, gain=0.7)
+    if scale_factor in (1, 2):
+        _swin_blocks(sd, g, "unet.swin4", C * 2, H, 2)
+        _linear(sd, g, "unet.up1.proj", C * 4, C * 2, gain=0.7)
+        _swin_blocks(sd, g, "unet.swin5", C, H, 2)
+        _linear(sd, g, "unet.to_image.proj", out_channels * scale_factor ** 2, C, gain=0.08)
+    else:
+        _linear(sd, g, "unet.proj2", C * 2, C, gain=0.7)
+        _swin_blocks(sd, g, "unet.swin4", C * 2, H, 2)
+        _linear(sd, g, "unet.up1.proj", C * 2 * 4, C * 2, gain=0.7)
+        _swin_blocks(sd, g, "unet.swin5", C * 2, H, 2)
+        _linear(sd, g, "unet.to_image.proj", out_channels * scale_factor ** 2, C * 2, gain=0.08)
+    sd["unet.to_image.proj.bias"] = torch.full_like(sd["unet.to_image.proj.bias"], 0.5) \
+        + _normal(g, sd["unet.to_image.proj.bias"].shape, 0.05)
+    return sd
+
+
+# ----------------------------------------------------------------------------
+# Synthetic images / depth (SURVEY.md section 8d "Value distributions / seeds")
+# ----------------------------------------------------------------------------
+
+def synth_image(seed, c, h, w, smooth=True):
+    """Uniform noise image in [0,1]; ``smooth`` mixes in low-frequency content."""
+    g = _gen(seed)
+    x = torch.rand((c, h, w), generator=g, dtype=torch.float32)
+    if smooth:
+        import torch.nn.functional as F
+        lo = torch.rand((1, c, max(h // 16, 2), max(w // 16, 2)), generator=g, dtype=torch.float32)
+        lo = F.interpolate(lo, size=(h, w), mode="bilinear", align_corners=False)[0]
+        x = (0.25 * x + 0.75 * lo).clamp(0, 1)
+    return x
+
+
+def synth_depth(seed, b, h, w, boxes=True):
+    """Smooth depth in [0,1] plus the reference _bench box pattern
+    (iw3/forward_warp.py:311-316) so holes/layered holes occur."""
+    import torch.nn.functional as F
+    g = _gen(seed)
+    d = torch.rand((b, 1, max(h // 24, 2), max(w // 24, 2)), generator=g, dtype=torch.float32)
+    d = F.interpolate(d, size=(h, w), mode="bicubic", align_corners=False)
+    d = d + torch.rand((b, 1, h, w), generator=g, dtype=torch.float32) * 1e-3  # break exact ties
+    if boxes:
+        y0, y1 = h // 4, h // 4 + h // 3
+        x0, x1 = w // 4, w // 4 + w // 4
+        d[:, :, y0:y1, x0:x1] += 1.0
+        y0, y1 = h // 2, h // 2 + h // 4
+        x0, x1 = w // 2 + w // 8, w // 2 + w // 8 + w // 5
+        d[:, :, y0:y1, x0:x1] += 0.5
+    mn = d.amin(dim=(1, 2, 3), keepdim=True)
+    mx = d.amax(dim=(1, 2, 3), keepdim=True)
+    return ((d - mn) / (mx - mn)).contiguous()

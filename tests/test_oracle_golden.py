@@ -1,0 +1,166 @@
+"""Pin the CPU oracle to the committed outputs of the real reference
+(tests/golden/*.npz, produced by oracle/gen_golden.py).  CPU only."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from nunif_b200 import synth
+from oracle import seam_blending as osb
+from oracle import cunet as ocu
+from oracle import swin_unet as osw
+from oracle import iw3 as oiw
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+torch.set_grad_enabled(False)
+
+
+def load(name):
+    return {k: v for k, v in np.load(os.path.join(G, name + ".npz")).items()}
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def maxdiff(a, b):
+    return float((t(a).double() - t(b).double()).abs().max())
+
+
+def test_create_config_bit_exact():
+    g = load("seam_config")
+    for case, want in zip(g["cases"], g["configs"]):
+        h, w, scale, offset, tile, blend = (int(v) for v in case)
+        p = osb.create_config(h, w, scale, offset, tile, blend)
+        got = [p["y_h"], p["y_w"], p["h_blocks"], p["w_blocks"], *p["pad"],
+               p["y_buffer_h"], p["y_buffer_w"], p["input_tile_step"], p["output_tile_step"]]
+        assert got == [int(v) for v in want], (case, got, want)
+
+
+def test_survey_table_counts():
+    # swin4x@256: 4K 10x17=170, 8K 19x33=627; upcunet 4K 10x18
+    p = osb.create_config(2160, 3840, 4, 32, 256, 16)
+    assert (p["h_blocks"], p["w_blocks"], p["input_tile_step"]) == (10, 17, 236)
+    p = osb.create_config(4320, 7680, 2, 16, 256, 8)
+    assert (p["h_blocks"], p["w_blocks"]) == (19, 33)
+    p = osb.create_config(2160, 3840, 2, 36, 256, 0)
+    assert (p["h_blocks"], p["w_blocks"], p["input_tile_step"]) == (10, 18, 220)
+
+
+def test_blend_filter_bit_exact():
+    g = load("seam_config")
+    for k, v in g.items():
+        if k.startswith("filter_"):
+            scale, offset, tile, blend = (int(s) for s in k.split("_")[1:])
+            f = osb.create_blend_filter(scale, offset, tile, blend, 3)
+            assert torch.equal(f, t(v)), k
+
+
+def test_find_valid_tile_size():
+    g = load("tile_size")
+    for q, c, s in zip(g["query"], g["cunet"], g["swin"]):
+        assert osb.find_valid_tile_size(osb.cunet_tile_validator, int(q)) == int(c)
+        assert osb.find_valid_tile_size(osb.swin_tile_validator, int(q)) == int(s)
+
+
+@pytest.mark.parametrize("name,up", [("upcunet", True), ("cunet", False)])
+def test_cunet_forward_and_render(name, up):
+    g = load(name)
+    sd = synth.upcunet_state_dict(0) if up else synth.cunet_state_dict(0)
+    assert torch.equal(synth.synth_image(11, 3, 104, 104).unsqueeze(0), t(g["x"]))
+    z = ocu.cunet_forward(sd, t(g["x"]), upscale=up)
+    assert maxdiff(z, g["z"]) < 2e-5
+    spec = ocu.UPCUNET if up else ocu.CUNET
+    y = osb.tiled_render(t(g["img"]), lambda b: ocu.cunet_forward(sd, b, upscale=up),
+                         spec["scale"], spec["offset"], spec["blend_size"], int(g["tile_size"]), int(g["batch_size"]))
+    assert y.shape == t(g["render"]).shape
+    assert maxdiff(y, g["render"]) < 2e-5
+
+
+def test_swin_unet_4x_family():
+    g = load("swin_unet_4x")
+    sd = synth.swin_unet_state_dict(0, 4)
+    x = t(g["x"])
+    assert maxdiff(osw.swin_unet_forward(sd, x, 4), g["z4"]) < 5e-5
+    assert maxdiff(osw.swin_unet_forward(sd, x, 4, 2), g["z2"]) < 5e-5
+    assert maxdiff(osw.swin_unet_forward(sd, x, 4, 4), g["z1"]) < 5e-5
+    y4 = osb.tiled_render(t(g["img"]), lambda b: osw.swin_unet_forward(sd, b, 4), 4, 32, 16, 64, 4)
+    assert maxdiff(y4, g["render4"]) < 5e-5
+    y2 = osb.tiled_render(t(g["img"]), lambda b: osw.swin_unet_forward(sd, b, 4, 2), 2, 16, 8, 64, 4)
+    assert maxdiff(y2, g["render2"]) < 5e-5
+    # closed-form (order independent) blend == raster-order reference
+    y4c = osb.tiled_render_closed_form(t(g["img"]), lambda b: osw.swin_unet_forward(sd, b, 4), 4, 32, 16, 64, 4)
+    assert maxdiff(y4c, g["render4"]) < 5e-5
+
+
+@pytest.mark.parametrize("sf", [1, 2])
+def test_swin_unet_native(sf):
+    g = load(f"swin_unet_{sf}x")
+    sd = synth.swin_unet_state_dict(0, sf)
+    assert maxdiff(osw.swin_unet_forward(sd, t(g["x"]), sf), g["z"]) < 5e-5
+
+
+def test_bicubic_aa_weights_match_aten():
+    import torch.nn.functional as F
+    x = torch.rand(1, 1, 48, 48)
+    for factor in (2, 4):
+        starts, w = osw.bicubic_aa_weights(48, 48 // factor)
+        # separable application
+        taps = w.shape[1]
+        idx = (starts.view(-1, 1) + torch.arange(taps).view(1, -1)).clamp(max=47)
+        tmp = (x[0, 0][:, idx] * w.view(1, -1, taps)).sum(-1)             # H, out
+        out = (tmp[idx, :] * w.view(-1, taps, 1)).sum(1)                   # out, out
+        ref = F.interpolate(x, size=(48 // factor,) * 2, mode="bicubic", align_corners=False, antialias=True)[0, 0]
+        assert float((out - ref).abs().max()) < 2e-6
+
+
+def test_backward_warp():
+    g = load("backward_warp")
+    c, d_lo, d_hi = t(g["c"]), t(g["d_lo"]), t(g["d_hi"])
+    for sv in ("both", "left", "right"):
+        l, r = oiw.apply_divergence_grid_sample(c, d_lo, 2.0, 0.5, sv)
+        assert maxdiff(l, g[f"bw_{sv}_l"]) < 2e-5 and maxdiff(r, g[f"bw_{sv}_r"]) < 2e-5
+    l, r = oiw.apply_divergence_grid_sample(c, d_hi, 5.0, 0.3, "both")
+    assert maxdiff(l, g["bw_hi_l"]) < 2e-5 and maxdiff(r, g["bw_hi_r"]) < 2e-5
+
+
+def test_forward_warp_bit_exact():
+    g = load("forward_warp")
+    c, d_lo, d_hi = t(g["c"]), t(g["d_lo"]), t(g["d_hi"])
+    for tag, depth, div, conv, wb in [("hi", d_hi, 4.0, 0.5, False), ("hi_wb", d_hi, 10.0, 0.3, True),
+                                      ("lo", d_lo, 4.0, 0.5, False)]:
+        for method in ("forward_fill", "forward"):
+            l, r, lm, rm = oiw.forward_warp(c, depth, div, conv, fill=(method == "forward_fill"),
+                                            return_mask=True, width_base=wb)
+            for got, key in ((l, "l"), (r, "r"), (lm, "lm"), (rm, "rm")):
+                assert maxdiff(got, g[f"fw_{tag}_{method}_{key}"]) == 0.0, (tag, method, key)
+    for sv in ("left", "right"):
+        l, r = oiw.forward_warp(c, d_hi, 2.0, 0.5, fill=True, synthetic_view=sv, width_base=False)
+        assert maxdiff(l, g[f"fw_{sv}_l"]) == 0.0 and maxdiff(r, g[f"fw_{sv}_r"]) == 0.0
+    l, r = oiw.forward_warp(t(g["cl"]), t(g["dl"]), 60.0, 0.0, fill=True, width_base=True)
+    assert maxdiff(l, g["fw_long_l"]) == 0.0 and maxdiff(r, g["fw_long_r"]) == 0.0
+    # the >100 px iteration cap really is exercised (unfilled cells stay negative)
+    assert (t(g["fw_long_l"]) < 0).any() or (t(g["fw_long_r"]) < 0).any()
+
+
+def test_dilation_minmax_mapper():
+    g = load("dilation")
+    x = t(g["x"])
+    for key in g:
+        if key.startswith("dil_"):
+            n = [int(v) for v in key.split("_")[1:]]
+            n = n[0] if len(n) == 1 else n
+            assert maxdiff(oiw.dilate_edge(x, n), g[key]) < 1e-5, key
+    mm = oiw.minmax_normalize(x[:1])[0]
+    assert maxdiff(mm, g["minmax0"]) == 0.0
+    assert maxdiff(oiw.mapper(mm, "div_6"), g["div_6"]) < 1e-6
+    assert maxdiff(oiw.mapper(mm, "div_1"), g["div_1"]) < 1e-6
+    with pytest.raises(ValueError):
+        oiw.edge_dilation_parse("3")
+
+
+def test_anaglyph():
+    g = load("anaglyph")
+    l, r = t(g["l"]), t(g["r"])
+    assert maxdiff(oiw.dubois(l, r, True), g["dubois"]) < 1e-6
+    assert maxdiff(oiw.dubois(l, r, False), g["dubois2"]) < 1e-6
