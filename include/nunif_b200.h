@@ -1,0 +1,182 @@
+/*
+ * nunif_b200 - C ABI of the B200-native engine for nunif's two hot paths.
+ *
+ * The reference (nagadomi/nunif) is pure Python; it has no FFI.  The boundary a
+ * maintainer binds is therefore "one C entry point per reference callable on
+ * the hot path" (SURVEY.md section 8b).  Each declaration cites the reference
+ * callable it replaces (paths relative to nagadomi/nunif @ d23721f).  The
+ * ctypes binding the reference would add is shown in INTEGRATION.md and
+ * implemented in nunif_b200/_lib.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host
+ *   - images are planar float32 CHW / BCHW exactly as the reference passes them
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - every function returns 0 on success, non-zero on error;
+ *     nb200_last_error() returns a thread-local message
+ *   - there is no CPU fallback: a call without a usable sm_100 device fails
+ */
+#ifndef NUNIF_B200_H
+#define NUNIF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_ABI_VERSION 1
+
+const char* nb200_last_error(void);
+int nb200_abi_version(void);
+/* device 0..n-1 must be compute capability 10.x; returns non-zero otherwise */
+int nb200_check_device(int device);
+/* number of kernels this library has launched in this process (bench `gpu_launches`) */
+uint64_t nb200_launch_count(void);
+
+/* ------------------------------------------------------------------ *
+ * Path A: tiled render (nunif/utils/seam_blending.py)
+ * ------------------------------------------------------------------ */
+
+typedef struct nb200_tile_config {
+    /* SeamBlending.create_config, seam_blending.py:109-143 */
+    int32_t y_h, y_w, h_blocks, w_blocks;
+    int32_t pad_l, pad_r, pad_t, pad_b;
+    int32_t y_buffer_h, y_buffer_w;
+    int32_t input_tile_step, output_tile_step;
+} nb200_tile_config;
+
+/* host-side integer planner; bit-exact with the reference. */
+int nb200_tile_config_create(int x_h, int x_w, int scale, int offset, int tile_size,
+                             int blend_size, nb200_tile_config* out_host);
+
+/* seam_blending.py:82-92: replicate-pad + unfold of tiles [tile0, tile0+n) in raster
+ * order into an NHWC fp16 tile batch  dst[n][T][T][cpad]  (channels >= C zero). */
+int nb200_tile_unfold(const float* x, int C, int H, int W, const nb200_tile_config* cfg_host,
+                      int tile_size, int tile0, int n, void* dst_nhwc_f16, int cpad, void* stream);
+
+/* seam_blending.py:156-174 (update) + :39-40 (get_output) in closed form:
+ *   out[C][y_h][y_w] = clamp( sum_t w_t*z_t / sum_t w_t , 0, 1 )
+ * over the (at most 4) tiles covering each output pixel, summed in raster tile order.
+ * z_all: fp16 planar [h_blocks*w_blocks][C][S][S], S = tile_size*scale - 2*offset.
+ * w = create_blend_filter (seam_blending.py:146-153) evaluated in closed form;
+ * blend_size==0 reproduces the plain store of :173. */
+int nb200_tile_gather_blend(const void* z_all_f16, int C, const nb200_tile_config* cfg_host,
+                            int scale, int offset, int tile_size, int blend_size,
+                            float* out, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Path A: models.  A model handle owns packed fp16 weights on one device.
+ * ------------------------------------------------------------------ */
+
+typedef struct nb200_model nb200_model;
+
+enum {
+    NB200_MODEL_UPCUNET = 1,        /* waifu2x.upcunet  (waifu2x/models/cunet.py:139-170) */
+    NB200_MODEL_CUNET = 2,          /* waifu2x.cunet    (cunet.py:173-203)                */
+    NB200_MODEL_SWIN_UNET_1X = 3,   /* waifu2x.swin_unet_1x (swin_unet.py:208-226)        */
+    NB200_MODEL_SWIN_UNET_2X = 4,   /* waifu2x.swin_unet_2x (swin_unet.py:229-251)        */
+    NB200_MODEL_SWIN_UNET_4X = 5    /* waifu2x.swin_unet_4x (swin_unet.py:261-303)        */
+};
+
+/* Create a model from named fp32 host tensors using the reference's state_dict
+ * keys (nunif/models/utils.py:42-74 load_model / load_state_dict).
+ * names[i] is the key, data_host[i] a contiguous float32 buffer of numel[i]
+ * elements.  Missing/extra keys are an error, like strict load_state_dict. */
+int nb200_model_create(int kind, int n_tensors, const char* const* names,
+                       const float* const* data_host, const int64_t* numel,
+                       int no_clip, nb200_model** out);
+void nb200_model_destroy(nb200_model* m);
+/* i2i contract of nunif/models/model.py:65-86 */
+int nb200_model_info(const nb200_model* m, int* scale, int* offset, int* blend_size);
+/* raw packed weight blob (for the one-time NCCL broadcast that replaces
+ * torch.nn.parallel.replicate, nunif/models/data_parallel.py:16,58) */
+int nb200_model_weight_blob(nb200_model* m, void** dev_ptr, size_t* bytes);
+
+/* model(minibatch) of seam_blending.py:94-95 under autocast fp16:
+ * x: NHWC fp16 [n][T][T][8] (from nb200_tile_unfold, channels 3..7 zero)
+ * z: planar fp16 [n][3][S][S], S = T*unet_scale/downscale - 2*offset (the reference's
+ *    model output is fp16 under autocast as well).
+ * downscale in {1,2,4}: 2/4 apply SwinUNetDownscaled (swin_unet.py:366-379). */
+int nb200_model_forward(nb200_model* m, const void* x_nhwc_f16, int n, int tile_size,
+                        int downscale, void* z_f16, void* stream);
+
+/* nunif.utils.render.tiled_render (render.py:8-19): whole image, device pointers. */
+int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, int W, int tile_size,
+                       int batch_size, int downscale, float* out, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Path B: iw3 depth post-processing and stereo warps
+ * ------------------------------------------------------------------ */
+
+enum { NB200_VIEW_BOTH = 0, NB200_VIEW_LEFT = 1, NB200_VIEW_RIGHT = 2 };
+enum { NB200_COMPOSE_NONE = 0,      /* separate left/right planar tensors            */
+       NB200_COMPOSE_SBS = 1,       /* iw3/utils.py:466-469 cat([L,R], dim=2)+clamp  */
+       NB200_COMPOSE_ANAGLYPH_DUBOIS = 2 /* iw3/anaglyph.py:51-92                    */ };
+
+/* iw3/backward_warp.py:96-121 apply_divergence_grid_sample.
+ * c: [B][3][H][W], depth: [B][1][h][w] (any resolution).
+ * compose NONE: left,right = [B][3][H][W]; SBS: left = [B][3][H][2W], right unused;
+ * ANAGLYPH: left = [B][3][H][W], right unused. */
+int nb200_backward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
+                        float divergence, float convergence, int synthetic_view, int compose,
+                        float* left, float* right, void* stream);
+
+/* iw3/forward_warp.py:246-256 apply_divergence_forward_warp (inconsistent_shift=False).
+ * depth: [B][1][h][w]; if (h,w)!=(H,W) it is resized like forward_warp.py:146-148.
+ * fill!=0 <=> method=="forward_fill".  masks may be NULL (return_mask=False).
+ * workspace: nb200_forward_warp_workspace() bytes (may be NULL if depth is full-res). */
+size_t nb200_forward_warp_workspace(int B, int H, int W, int h, int w);
+int nb200_forward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
+                       float divergence, float convergence, int fill, int synthetic_view,
+                       int width_base, int compose, float* left, float* right,
+                       float* left_mask, float* right_mask, void* workspace, void* stream);
+
+/* iw3/dilation.py:115-142 dilate_edge(x, [x_iter, y_iter]); x,out: [B][1][h][w];
+ * workspace: nb200_dilate_edge_workspace() bytes. */
+size_t nb200_dilate_edge_workspace(int B, int h, int w);
+int nb200_dilate_edge(const float* x, int B, int h, int w, int x_iter, int y_iter,
+                      float* out, void* workspace, void* stream);
+
+/* iw3/depth_scaler.py:4-17 with per-frame amin/amax (base_depth_model.py:176-194)
+ * followed by the mapper (iw3/mapper.py:29-32): mapper_c < 0 => "none",
+ * else distance_to_disparity(x, mapper_c) (div_6 => 0.6).  In place allowed. */
+int nb200_minmax_map(const float* depth, int B, int n_per_frame, float mapper_c,
+                     float* out, float* minmax_out /* [B][2] or NULL */, void* stream);
+
+/* iw3/anaglyph.py:51-92 on already-warped eyes: l,r,out [B][3][H][W] */
+int nb200_anaglyph_dubois(const float* l, const float* r, int B, int H, int W, int clip_before,
+                          float* out, void* stream);
+
+/* ------------------------------------------------------------------ *
+ * Low-level ops (exported for unit tests and micro-benchmarks; the model
+ * entry points above are sequences of these)
+ * ------------------------------------------------------------------ */
+
+/* F.interpolate(depth, size=(H,W), mode="bilinear", align_corners=True, antialias=True)
+ * as used at iw3/forward_warp.py:146-148 (the forward warp fuses this; this entry
+ * materialises it). depth [B][1][h][w] -> out [B][1][H][W]. */
+int nb200_depth_resize_aa(const float* depth, int B, int h, int w, int H, int W, float* out, void* stream);
+
+/* tcgen05 implicit GEMM on NHWC fp16 activations (csrc/gemm_tcgen05.cuh).
+ * kind: 0 linear over flattened pixels, 1 linear with 2-D tiling, 2 conv3x3 valid,
+ *       3 conv2x2 stride 2.  Wt: fp16 [N][taps*Cin] with K ordered (ky, kx, c).
+ * act: 0 none, 1 LeakyReLU(0.1), 2 GELU(erf), 3 ReLU.
+ * out_mode 1: N = 4*cout ordered (dy,dx,co), pixel-shuffle(2) scatter (ConvTranspose2d
+ * k2 s2 / Linear+pixel_shuffle).  res: optional residual read at (y+res_cy, x+res_cx). */
+int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci, int Cin, int kind,
+                        const void* Wt, int N, const float* bias, int act, void* out, int ldo,
+                        int out_mode, int cout, const void* res, int ldr, int res_H, int res_W,
+                        int res_cy, int res_cx, int res_before_act, void* stream);
+
+/* shifted-window attention core between the qkv and proj Linears
+ * (torchvision swin_transformer.py:166-221), window 6x6, 6 heads.
+ * qkv [B][H][W][3C] fp16 -> out [B][H][W][C] fp16; bias_table fp32 [121][6]. */
+int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B,
+                               int H, int W, int C, int heads, int shift, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUNIF_B200_H */

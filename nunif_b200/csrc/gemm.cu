@@ -1,0 +1,165 @@
+// Host side of the tcgen05 implicit-GEMM: tensor-map construction and dispatch.
+#include "gemm.h"
+#include "gemm_tcgen05.cuh"
+#include <mutex>
+
+namespace nb200 {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    // libcuda is resolved through the runtime so the library itself has no link-time
+    // dependency on the driver (it must load on a CPU-only box for the symbol checks).
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return fail("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+template <int BN, int BK>
+static int launch_t(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int m_tiles, int n_tiles) {
+    using Cfg = GemmCfg<BN, BK>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        NB_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    gemm_conv_kernel<BN, BK><<<dim3(m_tiles, n_tiles), GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    NB_LAUNCHED();
+    return 0;
+}
+
+template <int BK>
+static int launch_bn(int bn, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int m_tiles, int n_tiles) {
+    switch (bn) {
+        case 16: return launch_t<16, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 32: return launch_t<32, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 48: return launch_t<48, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 64: return launch_t<64, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 96: return launch_t<96, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 128: return launch_t<128, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 192: return launch_t<192, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 256: return launch_t<256, BK>(st, ta, tb, p, m_tiles, n_tiles);
+    }
+    return fail("unsupported BLOCK_N");
+}
+
+int pick_block_n(int N) {
+    static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
+    for (int c : cands)
+        if (N % c == 0) return c;
+    return 0;
+}
+
+int conv_gemm(cudaStream_t st, const ConvGemm& g) {
+    NB_CHECK(g.A && g.Wt && g.out, "null pointer");
+    NB_CHECK(g.Ci % 8 == 0, "input channel stride must be a multiple of 8");
+    NB_CHECK(g.N % 16 == 0, "N must be a multiple of 16 (pad the weights)");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int ktap;          // K per tap
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5];
+    const cuuint64_t e = 2;  // bytes per element
+    const cuuint64_t rs = (g.a_row_stride ? (cuuint64_t)g.a_row_stride : (cuuint64_t)g.Wi * g.Ci) * e;
+    const cuuint64_t is = (g.a_img_stride ? (cuuint64_t)g.a_img_stride * e : (cuuint64_t)g.Hi * rs);
+    switch (g.kind) {
+        case CG_LINEAR_FLAT: {
+            const long long M = (long long)g.B * g.Hi * g.Wi;
+            p.B = 1; p.Ho = 1; p.Wo = (int)M; p.TH = 1; p.TW = 128;
+            p.taps = 1; ktap = g.Cin;
+            dims[0] = g.Cin; dims[1] = M; dims[2] = 1; dims[3] = 1; dims[4] = 1;
+            strides[0] = g.Ci * e; strides[1] = M * g.Ci * e; strides[2] = strides[1]; strides[3] = strides[1];
+            break;
+        }
+        case CG_LINEAR_2D:
+        case CG_CONV3: {
+            const int kk = g.kind == CG_CONV3 ? 3 : 1;
+            p.B = g.B; p.Ho = g.Hi - (kk - 1); p.Wo = g.Wi - (kk - 1); p.TH = 8; p.TW = 16;
+            p.taps = kk * kk; ktap = g.Cin;
+            for (int t = 0; t < p.taps; ++t) { p.tap_dy[t] = t / kk; p.tap_dx[t] = t % kk; p.tap_dyi[t] = 0; }
+            dims[0] = g.Cin; dims[1] = g.Wi; dims[2] = 1; dims[3] = g.Hi; dims[4] = g.B;
+            strides[0] = g.Ci * e; strides[1] = rs; strides[2] = rs;
+            strides[3] = is;
+            break;
+        }
+        case CG_DOWN2: {
+            NB_CHECK(g.Hi % 2 == 0 && g.Wi % 2 == 0, "2x2 stride-2 conv needs even H and W");
+            NB_CHECK(g.Cin == g.Ci, "2x2 stride-2 conv needs a dense channel dimension");
+            p.B = g.B; p.Ho = g.Hi / 2; p.Wo = g.Wi / 2; p.TH = 8; p.TW = 16;
+            p.taps = 2; ktap = 2 * g.Cin;
+            for (int t = 0; t < 2; ++t) { p.tap_dy[t] = 0; p.tap_dx[t] = 0; p.tap_dyi[t] = t; }
+            dims[0] = 2 * g.Cin; dims[1] = g.Wi / 2; dims[2] = 2; dims[3] = g.Hi / 2; dims[4] = g.B;
+            strides[0] = 2 * g.Ci * e; strides[1] = rs; strides[2] = 2 * rs;
+            strides[3] = is;
+            break;
+        }
+        default: return fail("conv_gemm: unknown kind");
+    }
+    NB_CHECK(ktap % 32 == 0, "K per tap must be a multiple of 32");
+    const int BK = (ktap % 64 == 0) ? 64 : 32;
+    p.cpt = ktap / BK;
+    p.tiles_x = cdiv(p.Wo, p.TW);
+    p.tiles_y = cdiv(p.Ho, p.TH);
+    p.N = g.N;
+    p.bias = g.bias; p.act = g.act; p.out = g.out; p.ldo = g.ldo; p.out_mode = g.out_mode; p.cout = g.cout;
+    p.res = g.res; p.ldr = g.ldr; p.res_H = g.res_H; p.res_W = g.res_W; p.res_cy = g.res_cy; p.res_cx = g.res_cx;
+    p.res_before_act = g.res_before_act;
+    if (g.kind == CG_LINEAR_FLAT && g.res) { p.res_H = 1; p.res_W = p.Wo; p.res_cy = p.res_cx = 0; }
+    if (g.out_mode == OUT_PIXSHUF2) {
+        NB_CHECK(g.kind != CG_LINEAR_FLAT, "pixel-shuffle output needs 2-D tiling");
+        NB_CHECK(g.cout % 16 == 0 && g.N == 4 * g.cout, "pixel-shuffle: N must be 4*cout, cout % 16 == 0");
+    }
+    NB_CHECK(g.ldo % 8 == 0 && (!g.res || g.ldr % 8 == 0), "channel strides must be multiples of 8");
+    const int bn = pick_block_n(g.N);
+    NB_CHECK(bn > 0, "no BLOCK_N divides N");
+    box[0] = BK; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
+    CUtensorMap ta, tb;
+    if (encode(&ta, g.A, 5, dims, strides, box, BK * 2)) return 1;
+    const int K = p.taps * ktap;
+    cuuint64_t bdims[2] = {(cuuint64_t)K, (cuuint64_t)g.N};
+    cuuint64_t bstr[1] = {(cuuint64_t)K * e};
+    cuuint32_t bbox[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+    if (encode(&tb, g.Wt, 2, bdims, bstr, bbox, BK * 2)) return 1;
+    const int m_tiles = p.tiles_x * p.tiles_y * p.B, n_tiles = g.N / bn;
+    return BK == 64 ? launch_bn<64>(bn, st, ta, tb, p, m_tiles, n_tiles) : launch_bn<32>(bn, st, ta, tb, p, m_tiles, n_tiles);
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+// Low-level op exposed for unit tests and micro-benchmarks (see include/nunif_b200.h).
+extern "C" int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci, int Cin, int kind, const void* Wt, int N,
+                                   const float* bias, int act, void* out, int ldo, int out_mode, int cout,
+                                   const void* res, int ldr, int res_H, int res_W, int res_cy, int res_cx,
+                                   int res_before_act, void* stream) {
+    ConvGemm g;
+    g.A = (const __half*)A; g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Cin = Cin; g.kind = kind;
+    g.Wt = (const __half*)Wt; g.N = N; g.bias = bias; g.act = act; g.out = (__half*)out; g.ldo = ldo;
+    g.out_mode = out_mode; g.cout = cout; g.res = (const __half*)res; g.ldr = ldr; g.res_H = res_H; g.res_W = res_W;
+    g.res_cy = res_cy; g.res_cx = res_cx; g.res_before_act = res_before_act;
+    return conv_gemm((cudaStream_t)stream, g);
+}

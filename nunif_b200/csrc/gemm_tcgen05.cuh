@@ -1,0 +1,314 @@
+// tcgen05 implicit-GEMM for NHWC fp16 activations (sm_100a).
+//
+//   D[m, n] = act( sum_taps sum_c A[pixel(m) + tap, c] * Wt[n, tap, c] + bias[n] ) (+ residual)
+//
+// One kernel covers every dense contraction on path A:
+//   * Linear layers of the Swin blocks (1 tap, "pixel" = token)            swin_transformer.py:177,228,444
+//   * 3x3 valid convolutions of CUNet / the Swin patch stem (9 taps)       cunet.py:14-17,38,41 ; swin_unet.py:133-136
+//   * 2x2 stride-2 convolutions (2 taps over a (2C, W/2, 2, H/2, B) view)  cunet.py:36,78,80 ; swin_unet.py:49
+//   * ConvTranspose 2x2 s2 / Linear+pixel_shuffle(2) (N = 4*Cout, scatter) cunet.py:38,82,84 ; swin_unet.py:69-82
+//
+// Structure (Blackwell native):
+//   warp 0   : TMA producer - one 5-D box load per (tap, channel chunk) for A, one 2-D box for B,
+//              128B/64B hardware swizzle, mbarrier complete_tx
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 per instr),
+//              tcgen05.commit releases smem stages and finally signals the epilogue
+//   warps 2-5: epilogue - tcgen05.ld accumulator rows, bias + activation (+ residual), fp16 NHWC store
+// Non-persistent, one 128 x BLOCK_N output tile per CTA; shared memory is sized so that two CTAs
+// are co-resident per SM, which overlaps one tile's epilogue with the next tile's loads.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+namespace nb200 {
+
+enum : int { ACT_NONE = 0, ACT_LRELU01 = 1, ACT_GELU = 2, ACT_RELU = 3 };
+enum : int { OUT_NHWC = 0, OUT_PIXSHUF2 = 1 };
+
+struct GemmParams {
+    // output tiling: the M dimension is (b, y, x) over Ho x Wo pixels, tiled TH x TW (TH*TW == 128)
+    int B, Ho, Wo, TH, TW, tiles_x, tiles_y;
+    int N;               // output channels (GEMM N)
+    int taps, cpt;       // taps and BK-chunks per tap (K = taps*cpt*BK)
+    int8_t tap_dx[16], tap_dy[16], tap_dyi[16];
+    // epilogue
+    const float* bias;   // [N] or null
+    int act;
+    __half* out;         // NHWC fp16
+    int ldo;             // channel stride (elements per pixel) of out
+    int out_mode, cout;  // OUT_PIXSHUF2: N = 4*cout, out is [B][2Ho][2Wo][ldo]
+    const __half* res;   // optional residual, NHWC [B][res_H][res_W][ldr], read at (y+res_cy, x+res_cx)
+    int ldr, res_H, res_W, res_cy, res_cx;
+    int res_before_act;  // 0: out = act(acc+bias) + res ; 1: out = act(acc+bias+res)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    // bounded spin: a protocol bug traps instead of hanging the GPU
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf("nb200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2 : (SWIZZLE_BYTES == 64 ? 4 : 6);
+    constexpr uint64_t sbo = (8 * SWIZZLE_BYTES) >> 4;  // 8 rows of one swizzle span
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_LRELU01: return v > 0.f ? v : 0.1f * v;
+        case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // nn.GELU (erf form)
+        case ACT_RELU: return fmaxf(v, 0.f);
+        default: return v;
+    }
+}
+
+constexpr int GEMM_THREADS = 192;
+
+template <int BLOCK_N, int BK>
+struct GemmCfg {
+    static constexpr int SWIZZLE = BK * 2;  // bytes per K-row of a stage: 128 (BK=64) or 64 (BK=32)
+    static constexpr int A_BYTES = 128 * BK * 2;
+    static constexpr int B_BYTES = BLOCK_N * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+    static constexpr int STAGES = (98304 / STAGE_BYTES) < 2 ? 2 : ((98304 / STAGE_BYTES) > 6 ? 6 : (98304 / STAGE_BYTES));
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
+};
+
+template <int BLOCK_N, int BK>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, BK>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tx_i = tile % p.tiles_x;
+    const int ty_i = (tile / p.tiles_x) % p.tiles_y;
+    const int b = tile / (p.tiles_x * p.tiles_y);
+    const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
+    const int n0 = blockIdx.y * BLOCK_N;
+    const int k_iters = p.taps * p.cpt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            for (int it = 0; it < k_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int tap = it / p.cpt, ch = it - tap * p.cpt;
+                uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                uint8_t* sb = sa + Cfg::A_BYTES;
+                mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_5d(&tmA, &full_bar[s], sa, ch * BK, x0 + p.tap_dx[tap], p.tap_dyi[tap], y0 + p.tap_dy[tap], b);
+                tma_load_2d(&tmB, &full_bar[s], sb, it * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_f16(BLOCK_N);
+        for (int it = 0; it < k_iters; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t ad = make_kmajor_desc<Cfg::SWIZZLE>(sa + k * 32);
+                    const uint64_t bd = make_kmajor_desc<Cfg::SWIZZLE>(sb + k * 32);
+                    umma_f16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);                         // frees the smem stage when the MMAs retire
+                if (it == k_iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+        const int r = lane_grp * 32 + lane;       // accumulator row == pixel within the tile
+        const int ty = r / p.TW, tx = r - ty * p.TW;
+        const int y = y0 + ty, x = x0 + tx;
+        const bool valid = (y < p.Ho) && (x < p.Wo);
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        const size_t pix = ((size_t)b * p.Ho + y) * p.Wo + x;
+        const __half* res_row = nullptr;
+        if (p.res && valid)
+            res_row = p.res + (((size_t)b * p.res_H + (y + p.res_cy)) * p.res_W + (x + p.res_cx)) * p.ldr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(trow + c0, acc);
+            tmem_ld_wait();
+            const int n = n0 + c0;
+            if (!valid || n >= p.N) continue;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+            __half* dst;
+            const __half* rs = nullptr;
+            if (p.out_mode == OUT_PIXSHUF2) {
+                const int g = n / p.cout, co = n - g * p.cout;  // g = dy*2+dx
+                const size_t opix = ((size_t)b * (2 * p.Ho) + (2 * y + (g >> 1))) * (2 * p.Wo) + (2 * x + (g & 1));
+                dst = p.out + opix * p.ldo + co;
+                if (p.res) rs = p.res + (((size_t)b * p.res_H + (2 * y + (g >> 1) + p.res_cy)) * p.res_W + (2 * x + (g & 1) + p.res_cx)) * p.ldr + co;
+            } else {
+                dst = p.out + pix * p.ldo + n;
+                if (res_row) rs = res_row + n;
+            }
+            float rv[16];
+            if (rs) {
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rs));
+                const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rs) + 1);
+                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 a = __half22float2(h0[j]), c = __half22float2(h1[j]);
+                    rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = c.x; rv[8 + 2 * j + 1] = c.y;
+                }
+            }
+            __align__(16) __half2 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a0 = v[2 * j], a1 = v[2 * j + 1];
+                if (rs && p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
+                if (p.act != ACT_NONE) {
+                    // the reference applies the activation to the fp16 Linear/Conv output (autocast)
+                    a0 = apply_act(__half2float(__float2half_rn(a0)), p.act);
+                    a1 = apply_act(__half2float(__float2half_rn(a1)), p.act);
+                }
+                if (rs && !p.res_before_act) {
+                    // the reference adds two fp16 tensors: round the branch output first
+                    a0 = __half2float(__float2half_rn(a0)) + rv[2 * j];
+                    a1 = __half2float(__float2half_rn(a1)) + rv[2 * j + 1];
+                }
+                o[j] = __floats2half2_rn(a0, a1);
+            }
+            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
+            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace nb200

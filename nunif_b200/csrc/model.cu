@@ -1,0 +1,492 @@
+// Model containers: weight packing from the reference's state_dict keys and the
+// forward passes of SwinUNet (swin_unet.py:119-199) and CUNet/UpCUNet (cunet.py:10-203)
+// expressed as sequences of the sm_100a kernels.  Also the whole-image tiled render.
+#include "common.cuh"
+#include "gemm.h"
+#include "gemm_tcgen05.cuh"
+#include "swin_kernels.h"
+#include "cunet_kernels.h"
+#include "../../include/nunif_b200.h"
+#include <map>
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cmath>
+#include <memory>
+
+namespace nb200 {
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+struct HostTensor {
+    const float* data;
+    int64_t numel;
+    bool used;
+};
+
+struct Packer {
+    std::map<std::string, HostTensor> src;
+    std::vector<uint8_t> blob;
+    std::string err;
+
+    const float* get(const std::string& name, int64_t numel) {
+        auto it = src.find(name);
+        if (it == src.end()) {
+            if (err.empty()) err = "missing key in state_dict: " + name;
+            return nullptr;
+        }
+        if (it->second.numel != numel) {
+            if (err.empty())
+                err = "size mismatch for " + name + ": expected " + std::to_string(numel) + " elements, got " +
+                      std::to_string(it->second.numel);
+            return nullptr;
+        }
+        it->second.used = true;
+        return it->second.data;
+    }
+    void mark(const std::string& name) {
+        auto it = src.find(name);
+        if (it != src.end()) it->second.used = true;
+    }
+    size_t reserve(size_t bytes) {
+        size_t off = (blob.size() + 255) & ~(size_t)255;
+        blob.resize(off + bytes, 0);
+        return off;
+    }
+    size_t add_f16(const std::vector<float>& v) {
+        size_t off = reserve(v.size() * 2);
+        __half* d = reinterpret_cast<__half*>(blob.data() + off);
+        for (size_t i = 0; i < v.size(); ++i) d[i] = __float2half_rn(v[i]);
+        return off;
+    }
+    size_t add_f32(const std::vector<float>& v) {
+        size_t off = reserve(v.size() * 4);
+        memcpy(blob.data() + off, v.data(), v.size() * 4);
+        return off;
+    }
+};
+
+struct Lin {  // a packed GEMM operand: Wt [N][K] fp16 + bias [N] fp32
+    size_t w = 0, b = 0;
+    int N = 0, K = 0;
+};
+
+// Linear: weight [N][K]
+static Lin pack_linear(Packer& pk, const std::string& name, int N, int K, int n_pad = 0) {
+    Lin l;
+    l.N = n_pad ? n_pad : N;
+    l.K = K;
+    const float* w = pk.get(name + ".weight", (int64_t)N * K);
+    const float* b = pk.get(name + ".bias", N);
+    if (!w || !b) return l;
+    std::vector<float> wv((size_t)l.N * K, 0.f), bv(l.N, 0.f);
+    memcpy(wv.data(), w, (size_t)N * K * 4);
+    memcpy(bv.data(), b, (size_t)N * 4);
+    l.w = pk.add_f16(wv);
+    l.b = pk.add_f32(bv);
+    return l;
+}
+// Linear followed by pixel_shuffle(2): rows reordered so n = (dy*2+dx)*cout + co  (F.pixel_shuffle: c*4 + dy*2 + dx)
+static Lin pack_linear_pixshuf2(Packer& pk, const std::string& name, int cout, int K) {
+    Lin l;
+    l.N = 4 * cout;
+    l.K = K;
+    const float* w = pk.get(name + ".weight", (int64_t)4 * cout * K);
+    const float* b = pk.get(name + ".bias", 4 * cout);
+    if (!w || !b) return l;
+    std::vector<float> wv((size_t)l.N * K), bv(l.N);
+    for (int co = 0; co < cout; ++co)
+        for (int g = 0; g < 4; ++g) {
+            memcpy(&wv[((size_t)g * cout + co) * K], &w[((size_t)co * 4 + g) * K], (size_t)K * 4);
+            bv[g * cout + co] = b[co * 4 + g];
+        }
+    l.w = pk.add_f16(wv);
+    l.b = pk.add_f32(bv);
+    return l;
+}
+// Conv2d weight [Cout][Cin][kh][kw] -> [Cout][kh][kw][cin_pad]
+static Lin pack_conv(Packer& pk, const std::string& name, int cout, int cin, int kh, int kw, int cin_pad = 0, int cout_pad = 0) {
+    Lin l;
+    if (!cin_pad) cin_pad = cin;
+    l.N = cout_pad ? cout_pad : cout;
+    l.K = kh * kw * cin_pad;
+    const float* w = pk.get(name + ".weight", (int64_t)cout * cin * kh * kw);
+    const float* b = pk.get(name + ".bias", cout);
+    if (!w || !b) return l;
+    std::vector<float> wv((size_t)l.N * l.K, 0.f), bv(l.N, 0.f);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int y = 0; y < kh; ++y)
+                for (int x = 0; x < kw; ++x)
+                    wv[(size_t)co * l.K + ((size_t)y * kw + x) * cin_pad + ci] = w[(((size_t)co * cin + ci) * kh + y) * kw + x];
+    memcpy(bv.data(), b, (size_t)cout * 4);
+    l.w = pk.add_f16(wv);
+    l.b = pk.add_f32(bv);
+    return l;
+}
+// ConvTranspose2d(k=2, s=2) weight [Cin][Cout][2][2] -> rows n = (dy*2+dx)*cout + co, K = cin
+static Lin pack_convT2(Packer& pk, const std::string& name, int cin, int cout) {
+    Lin l;
+    l.N = 4 * cout;
+    l.K = cin;
+    const float* w = pk.get(name + ".weight", (int64_t)cin * cout * 4);
+    const float* b = pk.get(name + ".bias", cout);
+    if (!w || !b) return l;
+    std::vector<float> wv((size_t)l.N * cin), bv(l.N);
+    for (int g = 0; g < 4; ++g)
+        for (int co = 0; co < cout; ++co) {
+            for (int ci = 0; ci < cin; ++ci) wv[((size_t)g * cout + co) * cin + ci] = w[((size_t)ci * cout + co) * 4 + g];
+            bv[g * cout + co] = b[co];
+        }
+    l.w = pk.add_f16(wv);
+    l.b = pk.add_f32(bv);
+    return l;
+}
+// first 3x3 conv from 3 channels, fp32 [27][cout_pad] with k = (ky*3+kx)*3 + ci
+static Lin pack_stem(Packer& pk, const std::string& name, int cout, int cout_pad) {
+    Lin l;
+    l.N = cout_pad;
+    l.K = 27;
+    const float* w = pk.get(name + ".weight", (int64_t)cout * 27);
+    const float* b = pk.get(name + ".bias", cout);
+    if (!w || !b) return l;
+    std::vector<float> wv((size_t)27 * cout_pad, 0.f), bv(cout_pad, 0.f);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < 3; ++ci)
+            for (int k = 0; k < 9; ++k) {
+                // the stem reads fp16 inputs and the reference runs this conv in fp16 with fp32 accumulate:
+                // keep the weights at fp16 precision
+                wv[(size_t)(k * 3 + ci) * cout_pad + co] = __half2float(__float2half_rn(w[((size_t)co * 3 + ci) * 9 + k]));
+            }
+    memcpy(bv.data(), b, (size_t)cout * 4);
+    l.w = pk.add_f32(wv);
+    l.b = pk.add_f32(bv);
+    return l;
+}
+
+struct SwinBlockW {
+    Lin qkv, proj, fc1, fc2;
+    size_t table = 0;
+    int C = 0, shift = 0;
+};
+
+struct SwinW {
+    int C = 96, r = 4, cs = 48;
+    Lin stem, conv2, down1, down2, up2, up1, proj2, toimg;
+    std::vector<SwinBlockW> s1, s2, s3, s4, s5;
+};
+
+struct CUNetW;  // cunet_model.inl
+
+}  // namespace nb200
+
+using namespace nb200;
+
+struct nb200_model {
+    int kind = 0, no_clip = 0, device = 0;
+    int scale = 1, offset = 0, blend = 0;
+    uint8_t* blob = nullptr;
+    size_t blob_bytes = 0;
+    SwinW sw;
+    std::shared_ptr<CUNetW> cu;
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    template <typename T>
+    T* at(size_t off) const { return reinterpret_cast<T*>(blob + off); }
+    int ensure_ws(size_t bytes) {
+        if (bytes <= ws_bytes) return 0;
+        if (ws) cudaFree(ws);
+        ws = nullptr;
+        ws_bytes = 0;
+        NB_CUDA(cudaMalloc((void**)&ws, bytes));
+        ws_bytes = bytes;
+        return 0;
+    }
+};
+
+namespace nb200 {
+
+static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std::string& prefix, int C, int layers) {
+    for (int i = 0; i < layers; ++i) {
+        SwinBlockW b;
+        const std::string p = prefix + ".block." + std::to_string(i);
+        b.C = C;
+        b.shift = (i % 2 == 0) ? 0 : 3;  // swin_unet.py:30
+        b.qkv = pack_linear(pk, p + ".attn.qkv", 3 * C, C);
+        b.proj = pack_linear(pk, p + ".attn.proj", C, C);
+        b.fc1 = pack_linear(pk, p + ".mlp.0", 2 * C, C);
+        b.fc2 = pack_linear(pk, p + ".mlp.3", C, 2 * C);
+        const float* t = pk.get(p + ".attn.relative_position_bias_table", 121 * 6);
+        if (t) b.table = pk.add_f32(std::vector<float>(t, t + 121 * 6));
+        pk.mark(p + ".attn.relative_position_index");  // buffer; the kernel recomputes the index (swin_transformer.py:267-279)
+        out.push_back(b);
+    }
+}
+
+static void pack_swin(Packer& pk, SwinW& w, int r) {
+    const int C = 96;
+    w.C = C;
+    w.r = r;
+    w.cs = (3 * r * r + 15) / 16 * 16;
+    w.stem = pack_stem(pk, "unet.patch.0", C / 2, 64);
+    w.conv2 = pack_conv(pk, "unet.patch.2", C, C / 2, 3, 3, /*cin_pad=*/64);
+    pack_swin_blocks(pk, w.s1, "unet.swin1", C, 2);
+    w.down1 = pack_conv(pk, "unet.down1.conv", 2 * C, C, 2, 2);
+    pack_swin_blocks(pk, w.s2, "unet.swin2", 2 * C, 2);
+    w.down2 = pack_conv(pk, "unet.down2.conv", 2 * C, 2 * C, 2, 2);
+    pack_swin_blocks(pk, w.s3, "unet.swin3", 2 * C, 6);
+    w.up2 = pack_linear_pixshuf2(pk, "unet.up2.proj", 2 * C, 2 * C);
+    pack_swin_blocks(pk, w.s4, "unet.swin4", 2 * C, 2);
+    if (r == 4) {
+        w.proj2 = pack_linear(pk, "unet.proj2", 2 * C, C);
+        w.up1 = pack_linear_pixshuf2(pk, "unet.up1.proj", 2 * C, 2 * C);
+        pack_swin_blocks(pk, w.s5, "unet.swin5", 2 * C, 2);
+        w.toimg = pack_linear(pk, "unet.to_image.proj", 3 * r * r, 2 * C, w.cs);
+    } else {
+        w.up1 = pack_linear_pixshuf2(pk, "unet.up1.proj", C, 2 * C);
+        pack_swin_blocks(pk, w.s5, "unet.swin5", C, 2);
+        w.toimg = pack_linear(pk, "unet.to_image.proj", 3 * r * r, C, w.cs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward helpers
+// ---------------------------------------------------------------------------------------------
+struct Arena {
+    uint8_t* base;
+    size_t off = 0, cap;
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+static int linear_flat(cudaStream_t st, const nb200_model* m, const Lin& l, const __half* A, long long M, int lda, __half* out,
+                       int ldo, int act, const __half* res = nullptr, int ldr = 0) {
+    ConvGemm g;
+    g.A = A; g.B = 1; g.Hi = 1; g.Wi = (int)M; g.Ci = lda; g.Cin = l.K; g.kind = CG_LINEAR_FLAT;
+    g.Wt = m->at<__half>(l.w); g.N = l.N; g.bias = m->at<float>(l.b); g.act = act; g.out = out; g.ldo = ldo;
+    g.res = res; g.ldr = ldr;
+    return conv_gemm(st, g);
+}
+
+static int swin_block(cudaStream_t st, const nb200_model* m, const SwinBlockW& w, __half* X, int n, int H, __half* QKV, __half* ATT,
+                      __half* HID) {
+    const int C = w.C;
+    const long long T = (long long)n * H * H;
+    if (linear_flat(st, m, w.qkv, X, T, C, QKV, 3 * C, ACT_NONE)) return 1;
+    if (window_attention(st, QKV, m->at<float>(w.table), ATT, n, H, H, C, w.shift)) return 1;
+    if (linear_flat(st, m, w.proj, ATT, T, C, X, C, ACT_NONE, X, C)) return 1;       // x = x + attn(x)   :453
+    if (linear_flat(st, m, w.fc1, X, T, C, HID, 2 * C, ACT_GELU)) return 1;
+    if (linear_flat(st, m, w.fc2, HID, T, 2 * C, X, C, ACT_NONE, X, C)) return 1;    // x = x + mlp(x)    :454
+    return 0;
+}
+
+static size_t swin_ws_bytes(const SwinW& w, int n, int T) {
+    const size_t Hc = T - 16, t1 = (size_t)n * Hc * Hc, C = w.C;
+    const size_t C5 = w.r == 4 ? 2 * C : C;
+    size_t b = 0;
+    auto add = [&](size_t elems) { b += ((elems * 2 + 255) & ~(size_t)255) + 256; };
+    add((size_t)n * (T - 2) * (T - 2) * 64);  // S1
+    add(t1 * C);                              // X1
+    add(t1 * 3 * C5);                         // QKV (largest stage: swin5, or swin1)
+    add(t1 * C5);                             // ATT
+    add(t1 * 2 * C5);                         // HID
+    add(t1 / 4 * 2 * C);                      // X2
+    add(t1 / 16 * 2 * C);                     // X3
+    add(t1 / 4 * 2 * C);                      // X4
+    add(t1 * 2 * C);                          // P2
+    add(t1 * C5);                             // X5
+    add(t1 * w.cs);                           // Y
+    return b + 4096;
+}
+
+static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n, int T, int down, __half* z) {
+    const SwinW& w = m->sw;
+    NB_CHECK(T > 16 && (T - 16) % 12 == 0 && (T - 16) % 16 == 0, "invalid tile size for swin_unet (swin_unet.py:202-205)");
+    const int C = w.C, Hc = T - 16, H2 = Hc / 2, H3 = Hc / 4, S1w = T - 2;
+    const int C5 = w.r == 4 ? 2 * C : C;
+    if (m->ensure_ws(swin_ws_bytes(w, n, T))) return 1;
+    Arena a{m->ws, 0, m->ws_bytes};
+    const size_t t1 = (size_t)n * Hc * Hc;
+    __half* S1 = a.take<__half>((size_t)n * S1w * S1w * 64);
+    __half* X1 = a.take<__half>(t1 * C);
+    __half* QKV = a.take<__half>(t1 * 3 * C5);
+    __half* ATT = a.take<__half>(t1 * C5);
+    __half* HID = a.take<__half>(t1 * 2 * C5);
+    __half* X2 = a.take<__half>(t1 / 4 * 2 * C);
+    __half* X3 = a.take<__half>(t1 / 16 * 2 * C);
+    __half* X4 = a.take<__half>(t1 / 4 * 2 * C);
+    __half* P2 = a.take<__half>(t1 * 2 * C);
+    __half* X5 = a.take<__half>(t1 * C5);
+    __half* Y = a.take<__half>(t1 * w.cs);
+
+    // patch stem (swin_unet.py:133-137) + crop 6 (:182) folded into the second conv's addressing
+    if (stem_conv3x3(st, x, m->at<float>(w.stem.w), m->at<float>(w.stem.b), S1, n, T, T, 64, 64)) return 1;
+    {
+        ConvGemm g;
+        g.A = S1 + ((size_t)6 * S1w + 6) * 64; g.B = n; g.Hi = Hc + 2; g.Wi = Hc + 2; g.Ci = 64; g.Cin = 64;
+        g.a_row_stride = (long long)S1w * 64; g.a_img_stride = (long long)S1w * S1w * 64; g.kind = CG_CONV3;
+        g.Wt = m->at<__half>(w.conv2.w); g.N = C; g.bias = m->at<float>(w.conv2.b); g.act = ACT_LRELU01; g.out = X1; g.ldo = C;
+        if (conv_gemm(st, g)) return 1;
+    }
+    for (const auto& b : w.s1) if (swin_block(st, m, b, X1, n, Hc, QKV, ATT, HID)) return 1;   // x3
+    {   // down1 (swin_unet.py:45-62)
+        ConvGemm g;
+        g.A = X1; g.B = n; g.Hi = Hc; g.Wi = Hc; g.Ci = C; g.Cin = C; g.kind = CG_DOWN2;
+        g.Wt = m->at<__half>(w.down1.w); g.N = 2 * C; g.bias = m->at<float>(w.down1.b); g.out = X2; g.ldo = 2 * C;
+        if (conv_gemm(st, g)) return 1;
+    }
+    for (const auto& b : w.s2) if (swin_block(st, m, b, X2, n, H2, QKV, ATT, HID)) return 1;   // x4
+    {   // down2
+        ConvGemm g;
+        g.A = X2; g.B = n; g.Hi = H2; g.Wi = H2; g.Ci = 2 * C; g.Cin = 2 * C; g.kind = CG_DOWN2;
+        g.Wt = m->at<__half>(w.down2.w); g.N = 2 * C; g.bias = m->at<float>(w.down2.b); g.out = X3; g.ldo = 2 * C;
+        if (conv_gemm(st, g)) return 1;
+    }
+    for (const auto& b : w.s3) if (swin_block(st, m, b, X3, n, H3, QKV, ATT, HID)) return 1;   // x5
+    {   // up2 + skip: x = up2(x5) + x4   (swin_unet.py:190-191)
+        ConvGemm g;
+        g.A = X3; g.B = n; g.Hi = H3; g.Wi = H3; g.Ci = 2 * C; g.Cin = 2 * C; g.kind = CG_LINEAR_2D;
+        g.Wt = m->at<__half>(w.up2.w); g.N = w.up2.N; g.bias = m->at<float>(w.up2.b); g.out = X4; g.ldo = 2 * C;
+        g.out_mode = OUT_PIXSHUF2; g.cout = 2 * C; g.res = X2; g.ldr = 2 * C; g.res_H = H2; g.res_W = H2;
+        if (conv_gemm(st, g)) return 1;
+    }
+    for (const auto& b : w.s4) if (swin_block(st, m, b, X4, n, H2, QKV, ATT, HID)) return 1;
+    const __half* skip = X1;
+    if (w.r == 4) {  // proj2(x3), swin_unet.py:159,195
+        if (linear_flat(st, m, w.proj2, X1, (long long)t1, C, P2, 2 * C, ACT_NONE)) return 1;
+        skip = P2;
+    }
+    {   // up1 + skip
+        ConvGemm g;
+        g.A = X4; g.B = n; g.Hi = H2; g.Wi = H2; g.Ci = 2 * C; g.Cin = 2 * C; g.kind = CG_LINEAR_2D;
+        g.Wt = m->at<__half>(w.up1.w); g.N = w.up1.N; g.bias = m->at<float>(w.up1.b); g.out = X5; g.ldo = C5;
+        g.out_mode = OUT_PIXSHUF2; g.cout = C5; g.res = skip; g.ldr = C5; g.res_H = Hc; g.res_W = Hc;
+        if (conv_gemm(st, g)) return 1;
+    }
+    for (const auto& b : w.s5) if (swin_block(st, m, b, X5, n, Hc, QKV, ATT, HID)) return 1;
+    if (linear_flat(st, m, w.toimg, X5, (long long)t1, C5, Y, w.cs, ACT_NONE)) return 1;      // ToImage.proj :109
+    return to_image(st, Y, z, n, Hc, Hc, w.cs, w.r, down);
+}
+
+}  // namespace nb200
+
+#include "cunet_model.inl"
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
+                                  const int64_t* numel, int no_clip, nb200_model** out) {
+    NB_CHECK(out && names && data && numel, "null pointer");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_SWIN_UNET_4X, "unknown model kind");
+    int dev = 0;
+    NB_CUDA(cudaGetDevice(&dev));
+    if (nb200_check_device(dev)) return 1;
+    Packer pk;
+    for (int i = 0; i < n_tensors; ++i) pk.src[names[i]] = HostTensor{data[i], numel[i], false};
+    auto m = new nb200_model();
+    m->kind = kind;
+    m->no_clip = no_clip;
+    m->device = dev;
+    switch (kind) {
+        case NB200_MODEL_SWIN_UNET_1X: pack_swin(pk, m->sw, 1); m->scale = 1; m->offset = 8; m->blend = 4; break;    // swin_unet.py:213
+        case NB200_MODEL_SWIN_UNET_2X: pack_swin(pk, m->sw, 2); m->scale = 2; m->offset = 16; m->blend = 8; break;   // :234
+        case NB200_MODEL_SWIN_UNET_4X: pack_swin(pk, m->sw, 4); m->scale = 4; m->offset = 32; m->blend = 16; break;  // :267
+        case NB200_MODEL_UPCUNET: m->cu = pack_cunet(pk, true); m->scale = 2; m->offset = 36; m->blend = 0; break;   // cunet.py:144
+        case NB200_MODEL_CUNET: m->cu = pack_cunet(pk, false); m->scale = 1; m->offset = 28; m->blend = 0; break;    // cunet.py:178
+    }
+    if (pk.err.empty())
+        for (auto& kv : pk.src)
+            if (!kv.second.used) { pk.err = "unexpected key in state_dict: " + kv.first; break; }
+    if (!pk.err.empty()) {
+        delete m;
+        return fail(pk.err);
+    }
+    m->blob_bytes = pk.blob.size();
+    cudaError_t e = cudaMalloc((void**)&m->blob, m->blob_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(m->blob, pk.blob.data(), m->blob_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        delete m;
+        return fail(std::string("weight upload failed: ") + cudaGetErrorString(e));
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void nb200_model_destroy(nb200_model* m) {
+    if (!m) return;
+    if (m->blob) cudaFree(m->blob);
+    if (m->ws) cudaFree(m->ws);
+    delete m;
+}
+
+extern "C" int nb200_model_info(const nb200_model* m, int* scale, int* offset, int* blend_size) {
+    NB_CHECK(m, "null model");
+    if (scale) *scale = m->scale;
+    if (offset) *offset = m->offset;
+    if (blend_size) *blend_size = m->blend;
+    return 0;
+}
+
+extern "C" int nb200_model_weight_blob(nb200_model* m, void** dev_ptr, size_t* bytes) {
+    NB_CHECK(m && dev_ptr && bytes, "null pointer");
+    *dev_ptr = m->blob;
+    *bytes = m->blob_bytes;
+    return 0;
+}
+
+static int model_out_geometry(const nb200_model* m, int tile_size, int down, int* scale, int* offset, int* blend, int* S) {
+    NB_CHECK(down == 1 || down == 2 || down == 4, "downscale must be 1, 2 or 4");
+    NB_CHECK(down == 1 || m->kind == NB200_MODEL_SWIN_UNET_4X, "downscale is defined for swin_unet_4x only (swin_unet.py:339-387)");
+    // SwinUNetDownscaled: offset = 32//f, scale = 4//f, blend = 4*f (swin_unet.py:345-350)
+    *scale = down == 1 ? m->scale : 4 / down;
+    *offset = down == 1 ? m->offset : 32 / down;
+    *blend = down == 1 ? m->blend : 4 * down;
+    *S = tile_size * (*scale) - 2 * (*offset);
+    NB_CHECK(*S > 0, "tile_size too small");
+    return 0;
+}
+
+extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int tile_size, int downscale, void* z, void* stream) {
+    NB_CHECK(m && x && z, "null pointer");
+    NB_CHECK(n > 0, "empty batch");
+    int scale, offset, blend, S;
+    if (model_out_geometry(m, tile_size, downscale, &scale, &offset, &blend, &S)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->kind >= NB200_MODEL_SWIN_UNET_1X) return swin_forward(m, st, (const __half*)x, n, tile_size, downscale, (__half*)z);
+    return cunet_forward(m, st, (const __half*)x, n, tile_size, (__half*)z);
+}
+
+extern "C" int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, int W, int tile_size, int batch_size,
+                                  int downscale, float* out, void* stream) {
+    NB_CHECK(m && x && out, "null pointer");
+    NB_CHECK(C == 3, "models take 3-channel input");
+    NB_CHECK(batch_size > 0, "batch_size must be positive");
+    int scale, offset, blend, S;
+    if (model_out_geometry(m, tile_size, downscale, &scale, &offset, &blend, &S)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    nb200_tile_config cfg;
+    if (nb200_tile_config_create(H, W, scale, offset, tile_size, blend, &cfg)) return 1;
+    const int ntiles = cfg.h_blocks * cfg.w_blocks;
+    // frame-level buffers (stream-ordered): the unfolded tile batch and every tile's output
+    __half *xb = nullptr, *zall = nullptr;
+    const size_t xb_elems = (size_t)batch_size * tile_size * tile_size * 8, z_tile = (size_t)3 * S * S;
+    NB_CUDA(cudaMallocAsync((void**)&xb, xb_elems * 2, st));
+    NB_CUDA(cudaMallocAsync((void**)&zall, (size_t)ntiles * z_tile * 2, st));
+    int rc = 0;
+    for (int t0 = 0; t0 < ntiles && !rc; t0 += batch_size) {
+        const int nb = ntiles - t0 < batch_size ? ntiles - t0 : batch_size;
+        rc = nb200_tile_unfold(x, C, H, W, &cfg, tile_size, t0, nb, xb, 8, stream);
+        if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile, stream);
+    }
+    if (!rc) rc = nb200_tile_gather_blend(zall, C, &cfg, scale, offset, tile_size, blend, out, stream);
+    cudaFreeAsync(xb, st);
+    cudaFreeAsync(zall, st);
+    return rc;
+}

@@ -1,0 +1,151 @@
+// Tiling engine: integer planner, tile unfold (replicate pad fused), closed-form
+// overlap blend as a gather.
+//
+// Replaces nunif/utils/seam_blending.py:
+//   create_config :109-143  -> nb200_tile_config_create (host, integers, bit-exact)
+//   F.pad replicate :82 + per-tile slice copies :83-92 -> tile_unfold_kernel (one launch per batch)
+//   update :156-174 (5 elementwise passes per tile over two fp32 accumulators the size of
+//   the output) + get_output :39-40 -> tile_gather_blend_kernel: every output pixel gathers
+//   the <=4 tiles that cover it, out = clamp(sum w*z / sum w).  No accumulators exist at all;
+//   traffic = read each z once (fp16) + write the output once.
+#include "common.cuh"
+#include "../../include/nunif_b200.h"
+
+namespace nb200 {
+
+// dst[n][T][T][cpad] fp16; 8 channels per 16-byte store when cpad == 8.
+__global__ void __launch_bounds__(256) tile_unfold_kernel(const float* __restrict__ x, int C, int H, int W, int pad_l, int pad_t,
+                                                          int w_blocks, int step, int T, int tile0, int n, int cpad,
+                                                          __half* __restrict__ dst) {
+    const size_t total = (size_t)n * T * T;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int px = (int)(i % T);
+    const int py = (int)((i / T) % T);
+    const int k = (int)(i / ((size_t)T * T));
+    const int t = tile0 + k;
+    const int hi = t / w_blocks, wi = t % w_blocks;
+    // padded coordinate -> clamp-to-edge source coordinate (F.pad mode='replicate')
+    const int sy = min(max(hi * step + py - pad_t, 0), H - 1);
+    const int sx = min(max(wi * step + px - pad_l, 0), W - 1);
+    __half* d = dst + i * cpad;
+    if (cpad == 8) {
+        __align__(16) __half v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __float2half_rn(c < C ? __ldg(x + ((size_t)c * H + sy) * W + sx) : 0.f);
+        *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(v);
+    } else {
+        for (int c = 0; c < cpad; ++c) d[c] = __float2half_rn(c < C ? __ldg(x + ((size_t)c * H + sy) * W + sx) : 0.f);
+    }
+}
+
+struct BlendParams {
+    const __half* z;
+    float* out;
+    int C, S, y_h, y_w, h_blocks, w_blocks, step_out, blend;
+    float ring[65];  // ring[d] = weight at distance d from the tile edge, d < blend
+};
+
+__device__ __forceinline__ float blend_weight(const BlendParams& p, int u, int v) {
+    // create_blend_filter :146-153: ones inside, rings of 1-(i+1)/(blend+1) growing outward
+    int d = min(min(u, v), min(p.S - 1 - u, p.S - 1 - v));
+    return d >= p.blend ? 1.f : p.ring[d];
+}
+
+__global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y;
+    if (X >= p.y_w) return;
+    // tiles covering Y: hi with hi*step <= Y < hi*step + S
+    const int hi1 = min(Y / p.step_out, p.h_blocks - 1);
+    const int wi1 = min(X / p.step_out, p.w_blocks - 1);
+    int his[2], wis[2], nh = 0, nw = 0;
+    if (hi1 > 0 && Y - (hi1 - 1) * p.step_out < p.S) his[nh++] = hi1 - 1;
+    if (Y - hi1 * p.step_out < p.S) his[nh++] = hi1;
+    if (wi1 > 0 && X - (wi1 - 1) * p.step_out < p.S) wis[nw++] = wi1 - 1;
+    if (X - wi1 * p.step_out < p.S) wis[nw++] = wi1;
+    const size_t zplane = (size_t)p.S * p.S;
+    for (int c = 0; c < p.C; ++c) {
+        float num = 0.f, den = 0.f;
+        for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b) {
+                const int u = Y - his[a] * p.step_out, v = X - wis[b] * p.step_out;
+                const size_t t = (size_t)his[a] * p.w_blocks + wis[b];
+                const float zv = __half2float(p.z[(t * p.C + c) * zplane + (size_t)u * p.S + v]);
+                if (p.blend > 0) {
+                    const float w = blend_weight(p, u, v);
+                    num += w * zv;
+                    den += w;
+                } else {  // plain store, last tile in raster order wins (:173)
+                    num = zv;
+                    den = 1.f;
+                }
+            }
+        p.out[((size_t)c * p.y_h + Y) * p.y_w + X] = clamp01(num / den);
+    }
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+extern "C" int nb200_tile_config_create(int x_h, int x_w, int scale, int offset, int tile_size, int blend_size,
+                                        nb200_tile_config* out) {
+    NB_CHECK(out, "null pointer");
+    NB_CHECK(x_h > 0 && x_w > 0 && scale > 0 && offset >= 0 && tile_size > 0 && blend_size >= 0, "bad argument");
+    const int input_offset = (offset + scale - 1) / scale;       // math.ceil(offset / scale)
+    const int input_blend = (blend_size + scale - 1) / scale;    // math.ceil(blend_size / scale)
+    const int step = tile_size - (input_offset * 2 + input_blend);
+    NB_CHECK(step > 0, "tile_size too small for this offset/blend");
+    int h_blocks = 0, w_blocks = 0, input_h = 0, input_w = 0;
+    while (input_h < x_h + input_offset * 2) { input_h = h_blocks * step + tile_size; ++h_blocks; }
+    while (input_w < x_w + input_offset * 2) { input_w = w_blocks * step + tile_size; ++w_blocks; }
+    out->y_h = x_h * scale;
+    out->y_w = x_w * scale;
+    out->h_blocks = h_blocks;
+    out->w_blocks = w_blocks;
+    out->pad_l = input_offset;
+    out->pad_r = input_w - (x_w + input_offset);
+    out->pad_t = input_offset;
+    out->pad_b = input_h - (x_h + input_offset);
+    out->y_buffer_h = input_h * scale;
+    out->y_buffer_w = input_w * scale;
+    out->input_tile_step = step;
+    out->output_tile_step = step * scale;
+    return 0;
+}
+
+extern "C" int nb200_tile_unfold(const float* x, int C, int H, int W, const nb200_tile_config* cfg, int tile_size,
+                                 int tile0, int n, void* dst, int cpad, void* stream) {
+    NB_CHECK(x && cfg && dst, "null pointer");
+    NB_CHECK(C <= cpad, "cpad must be >= C");
+    NB_CHECK(tile0 >= 0 && n > 0 && tile0 + n <= cfg->h_blocks * cfg->w_blocks, "tile range out of bounds");
+    const size_t total = (size_t)n * tile_size * tile_size;
+    tile_unfold_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, C, H, W, cfg->pad_l, cfg->pad_t, cfg->w_blocks, cfg->input_tile_step, tile_size, tile0, n, cpad, (__half*)dst);
+    NB_LAUNCHED();
+    return 0;
+}
+
+extern "C" int nb200_tile_gather_blend(const void* z_all, int C, const nb200_tile_config* cfg, int scale, int offset,
+                                       int tile_size, int blend_size, float* out, void* stream) {
+    NB_CHECK(z_all && cfg && out, "null pointer");
+    NB_CHECK(blend_size >= 0 && blend_size <= 64, "blend_size out of range");
+    BlendParams p;
+    p.z = (const __half*)z_all;
+    p.out = out;
+    p.C = C;
+    p.S = tile_size * scale - 2 * offset;
+    p.y_h = cfg->y_h; p.y_w = cfg->y_w; p.h_blocks = cfg->h_blocks; p.w_blocks = cfg->w_blocks;
+    p.step_out = cfg->output_tile_step;
+    p.blend = blend_size;
+    NB_CHECK(p.S > 0 && p.S - p.step_out <= p.step_out, "tile overlap larger than the tile step is not supported");
+    for (int d = 0; d < blend_size; ++d) {
+        // ring index i = blend-1-d (outermost ring is added last); value = 1 - (1/(blend+1))*(i+1)
+        const int i = blend_size - 1 - d;
+        p.ring[d] = (float)(1.0 - (1.0 / (blend_size + 1)) * (i + 1));
+    }
+    tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
+    NB_LAUNCHED();
+    return 0;
+}

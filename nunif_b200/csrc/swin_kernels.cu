@@ -1,0 +1,279 @@
+// Non-GEMM kernels of the SwinUNet path (NHWC fp16 activations).
+//   stem_conv3x3_kernel     first 3x3 valid conv from the (3->8 padded) tile batch, LeakyReLU(0.1)
+//                           (swin_unet.py:133-134, cunet.py:14-15 conv.0); K=27 is too thin for tensor cores
+//   window_attention_kernel fused shifted-window attention core: roll + 6x6 partition + QK^T*scale +
+//                           relative-position bias + shift mask + softmax + PV + un-roll, all by index
+//                           arithmetic (torchvision swin_transformer.py:166-221 between the qkv and proj Linears)
+//   to_image_kernel         pixel_shuffle + clamp (+ bicubic-antialias /2,/4 + clamp) -> planar fp16 z
+//                           (swin_unet.py:108-115, :366-379)
+#include "common.cuh"
+#include "swin_kernels.h"
+
+namespace nb200 {
+
+// ---------------------------------------------------------------------------------------------
+// stem conv: x [n][Hi][Wi][8] fp16 -> out [n][Hi-2][Wi-2][ldo] fp16, channels >= cout written as 0
+// weights: wt [27][COUT_PAD] fp32 (k = (ky*3+kx)*3 + ci), bias [COUT_PAD] fp32 (zero padded)
+// ---------------------------------------------------------------------------------------------
+template <int COUT_PAD>
+__global__ void __launch_bounds__(128) stem_conv3x3_kernel(const __half* __restrict__ x, const float* __restrict__ wt,
+                                                           const float* __restrict__ bias, __half* __restrict__ out,
+                                                           int n, int Hi, int Wi, int ldo) {
+    __shared__ __align__(16) float sw[27 * COUT_PAD];
+    __shared__ __align__(16) float sb[COUT_PAD];
+    for (int i = threadIdx.x; i < 27 * COUT_PAD; i += blockDim.x) sw[i] = wt[i];
+    for (int i = threadIdx.x; i < COUT_PAD; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int Ho = Hi - 2, Wo = Wi - 2;
+    const size_t total = (size_t)n * Ho * Wo;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), b = (int)(i / ((size_t)Wo * Ho));
+    float in[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * Hi + oy + ky) * Wi + ox + kx) * 8));
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+            const float2 a = __half22float2(h[0]), c = __half22float2(h[1]);
+            in[(ky * 3 + kx) * 3 + 0] = a.x;
+            in[(ky * 3 + kx) * 3 + 1] = a.y;
+            in[(ky * 3 + kx) * 3 + 2] = c.x;
+        }
+    __half* o = out + i * ldo;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COUT_PAD; c0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * COUT_PAD + c0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * COUT_PAD + c0 + 4]);
+            acc[0] += in[k] * w0.x; acc[1] += in[k] * w0.y; acc[2] += in[k] * w0.z; acc[3] += in[k] * w0.w;
+            acc[4] += in[k] * w1.x; acc[5] += in[k] * w1.y; acc[6] += in[k] * w1.z; acc[7] += in[k] * w1.w;
+        }
+        __align__(16) __half2 hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0 = acc[2 * j], a1 = acc[2 * j + 1];
+            a0 = a0 > 0.f ? a0 : 0.1f * a0;
+            a1 = a1 > 0.f ? a1 : 0.1f * a1;
+            hv[j] = __floats2half2_rn(a0, a1);
+        }
+        *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(hv);
+    }
+}
+
+int stem_conv3x3(cudaStream_t st, const __half* x, const float* wt, const float* bias, __half* out, int n, int Hi, int Wi,
+                 int cout_pad, int ldo) {
+    NB_CHECK(ldo >= cout_pad && ldo % 8 == 0, "bad output stride");
+    const size_t total = (size_t)n * (Hi - 2) * (Wi - 2);
+    const unsigned blocks = (unsigned)cdiv64(total, 128);
+    if (cout_pad == 64) stem_conv3x3_kernel<64><<<blocks, 128, 0, st>>>(x, wt, bias, out, n, Hi, Wi, ldo);
+    else if (cout_pad == 32) stem_conv3x3_kernel<32><<<blocks, 128, 0, st>>>(x, wt, bias, out, n, Hi, Wi, ldo);
+    else return fail("stem_conv3x3: unsupported channel count");
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// window attention (6x6 windows, HEADS=6).  One CTA per window, one thread per (head, query).
+// qkv: [B][H][W][3C] fp16 (q | k | v, each head-major like torchvision's reshape :179-180)
+// out: [B][H][W][C] fp16 (pre-projection)
+// ---------------------------------------------------------------------------------------------
+constexpr int WS = 6, WTOK = 36, HEADS = 6;
+
+template <int D>  // head dim: 16 (C=96) or 32 (C=192)
+__global__ void __launch_bounds__(224) window_attention_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias_table,
+                                                               __half* __restrict__ out, int H, int W, int shift) {
+    constexpr int C = D * HEADS;
+    __shared__ __align__(16) __half sk[WTOK * C];
+    __shared__ __align__(16) __half sv[WTOK * C];
+    __shared__ float stab[121 * HEADS];
+    __shared__ int stok[WTOK];    // token -> flat pixel index (b*H + y)*W + x in the un-rolled map
+    __shared__ int sreg[WTOK];    // shift-mask region id (:193-203)
+    const int nww = W / WS;
+    const int wx = blockIdx.x % nww, wy = blockIdx.x / nww, b = blockIdx.y;
+    const int tid = threadIdx.x;
+    if (tid < WTOK) {
+        const int ry = wy * WS + tid / WS, rx = wx * WS + tid % WS;        // rolled coordinates
+        const int y = (ry + shift) % H, x = (rx + shift) % W;              // torch.roll(-shift) :166-167
+        stok[tid] = (b * H + y) * W + x;
+        int hr = 0, wr = 0;
+        if (shift > 0) {
+            hr = ry < H - WS ? 0 : (ry < H - shift ? 1 : 2);
+            wr = rx < W - WS ? 0 : (rx < W - shift ? 1 : 2);
+        }
+        sreg[tid] = hr * 3 + wr;
+    }
+    for (int i = tid; i < 121 * HEADS; i += blockDim.x) stab[i] = bias_table[i];
+    __syncthreads();
+    // stage K and V of the 36 tokens (16-byte vectors, coalesced per token row)
+    constexpr int VPT = C / 8;  // uint4 per token per matrix
+    for (int i = tid; i < WTOK * VPT; i += blockDim.x) {
+        const int t = i / VPT, v = i - t * VPT;
+        const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)stok[t] * (3 * C));
+        reinterpret_cast<uint4*>(sk)[t * VPT + v] = __ldg(src + VPT + v);
+        reinterpret_cast<uint4*>(sv)[t * VPT + v] = __ldg(src + 2 * VPT + v);
+    }
+    __syncthreads();
+    if (tid >= WTOK * HEADS) return;
+    const int head = tid / WTOK, q = tid - head * WTOK;
+    const float scale = (D == 16) ? 0.25f : 0.17677669529663687f;  // (C // heads) ** -0.5 (:187)
+    float qv[D];
+    {
+        const __half* qp = qkv + (size_t)stok[q] * (3 * C) + head * D;
+#pragma unroll
+        for (int j = 0; j < D; j += 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(qp + j));
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                // q * scale is an fp16 tensor op in the reference (autocast): round like it does
+                qv[j + 2 * k] = __half2float(__float2half_rn(f.x * scale));
+                qv[j + 2 * k + 1] = __half2float(__float2half_rn(f.y * scale));
+            }
+        }
+    }
+    const int qy = q / WS, qx = q - qy * WS, qreg = sreg[q];
+    float s[WTOK];
+    float mx = -1e30f;
+#pragma unroll
+    for (int k = 0; k < WTOK; ++k) {
+        const __half* kp = sk + k * C + head * D;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; j += 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(kp + j);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                acc += qv[j + 2 * e] * f.x + qv[j + 2 * e + 1] * f.y;
+            }
+        }
+        acc = __half2float(__float2half_rn(acc));  // fp16 matmul output (:188)
+        const int ky = k / WS, kx = k - ky * WS;
+        acc += stab[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head];  // :49-59,:190
+        if (sreg[k] != qreg) acc += -100.0f;                                                    // :204-209
+        s[k] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < WTOK; ++k) {
+        s[k] = __expf(s[k] - mx);
+        sum += s[k];
+    }
+    const float inv = 1.f / sum;
+    float o[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < WTOK; ++k) {
+        const float pk = __half2float(__float2half_rn(s[k] * inv));  // softmax output cast to fp16 for the PV matmul (:214)
+        const __half* vp = sv + k * C + head * D;
+#pragma unroll
+        for (int j = 0; j < D; j += 8) {
+            const uint4 v = *reinterpret_cast<const uint4*>(vp + j);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                o[j + 2 * e] += pk * f.x;
+                o[j + 2 * e + 1] += pk * f.y;
+            }
+        }
+    }
+    __half* op = out + (size_t)stok[q] * C + head * D;
+#pragma unroll
+    for (int j = 0; j < D; j += 8) {
+        __align__(16) __half2 hv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hv[e] = __floats2half2_rn(o[j + 2 * e], o[j + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(op + j) = *reinterpret_cast<const uint4*>(hv);
+    }
+}
+
+int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table, __half* out, int B, int H, int W, int C,
+                     int shift) {
+    NB_CHECK(H % WS == 0 && W % WS == 0, "feature map must be a multiple of the 6x6 window");
+    NB_CHECK(C == 96 || C == 192, "window attention supports C=96 (d=16) and C=192 (d=32)");
+    if (WS >= H) shift = 0;  // torchvision :151-155
+    dim3 grid((H / WS) * (W / WS), B);
+    if (C == 96) window_attention_kernel<16><<<grid, 224, 0, st>>>(qkv, bias_table, out, H, W, shift);
+    else window_attention_kernel<32><<<grid, 224, 0, st>>>(qkv, bias_table, out, H, W, shift);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ToImage tail: y [n][Hs][Ws][cs] fp16 with channel = c*r*r + dy*r + dx (F.pixel_shuffle) ->
+// z planar fp16 [n][3][S][S], S = Hs*r/down.  down>1: clamp, bicubic antialias (A=-0.5) resize, clamp.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cubic_aa(float x) {
+    const float a = -0.5f;
+    x = fabsf(x);
+    if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+    if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+    return 0.f;
+}
+
+__device__ __forceinline__ float shuffled_px(const __half* __restrict__ yb, int Ws, int cs, int r, int c, int Y, int X) {
+    const int ty = Y / r, dy = Y - ty * r, tx = X / r, dx = X - tx * r;
+    return __half2float(yb[((size_t)ty * Ws + tx) * cs + c * r * r + dy * r + dx]);
+}
+
+__global__ void __launch_bounds__(256) to_image_kernel(const __half* __restrict__ y, __half* __restrict__ z, int n, int Hs,
+                                                       int Ws, int cs, int r, int down) {
+    const int S_full = Hs * r, S = S_full / down;
+    const size_t total = (size_t)n * 3 * S * S;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int X = (int)(i % S), Y = (int)((i / S) % S), c = (int)((i / ((size_t)S * S)) % 3), b = (int)(i / ((size_t)3 * S * S));
+    const __half* yb = y + (size_t)b * Hs * Ws * cs;
+    float v;
+    if (down == 1) {
+        v = clamp01(shuffled_px(yb, Ws, cs, r, c, Y, X));
+    } else {
+        // ATen upsample_bicubic2d_aa, align_corners=False: scale = down, support = 2*scale
+        const float scale = (float)down, support = 2.f * scale, inv = 1.f / scale;
+        const float cy = scale * (Y + 0.5f), cx = scale * (X + 0.5f);
+        const int ymin = max((int)(cy - support + 0.5f), 0), ysz = min((int)(cy + support + 0.5f), S_full) - ymin;
+        const int xmin = max((int)(cx - support + 0.5f), 0), xsz = min((int)(cx + support + 0.5f), S_full) - xmin;
+        float wy[17], wx[17], ty = 0.f, tx = 0.f;
+        for (int k = 0; k < ysz; ++k) { wy[k] = cubic_aa((k + ymin - cy + 0.5f) * inv); ty += wy[k]; }
+        for (int k = 0; k < xsz; ++k) { wx[k] = cubic_aa((k + xmin - cx + 0.5f) * inv); tx += wx[k]; }
+        float acc = 0.f;
+        for (int a = 0; a < ysz; ++a) {
+            float row = 0.f;
+            for (int k = 0; k < xsz; ++k) row += clamp01(shuffled_px(yb, Ws, cs, r, c, ymin + a, xmin + k)) * (wx[k] / tx);
+            acc += row * (wy[a] / ty);
+        }
+        v = clamp01(acc);
+    }
+    z[i] = __float2half_rn(v);
+}
+
+int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws, int cs, int r, int down) {
+    NB_CHECK(down == 1 || down == 2 || down == 4, "downscale must be 1, 2 or 4");
+    NB_CHECK(Hs == Ws && (Hs * r) % down == 0, "bad ToImage geometry");
+    const size_t total = (size_t)n * 3 * (Hs * r / down) * (Ws * r / down);
+    to_image_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(y, z, n, Hs, Ws, cs, r, down);
+    NB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+extern "C" int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C,
+                                          int heads, int shift, void* stream) {
+    NB_CHECK(qkv && bias_table && out, "null pointer");
+    NB_CHECK(heads == HEADS, "only 6 heads are supported");
+    return window_attention((cudaStream_t)stream, (const __half*)qkv, bias_table, (__half*)out, B, H, W, C, shift);
+}

@@ -1,0 +1,14 @@
+"""B200-native mirror of the iw3 hot-path callables (reference: iw3/*.py).
+
+Same names, argument meaning and error behaviour as the reference functions so
+that ``iw3.utils.apply_divergence`` / ``postprocess_image`` can import these in
+place of the originals.  Every function requires CUDA tensors
+and dispatches to hand-written sm_100a kernels through the C ABI; there is no
+CPU path.
+"""
+from .backward_warp import apply_divergence_grid_sample  # noqa: F401
+from .forward_warp import apply_divergence_forward_warp  # noqa: F401
+from .dilation import dilate_edge, edge_dilation_parse, edge_dilation_is_enabled  # noqa: F401
+from .depth_scaler import minmax_normalize  # noqa: F401
+from .anaglyph import apply_anaglyph_redcyan  # noqa: F401
+from .stereo import stereo_sbs  # noqa: F401
