@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py - the driver's measurement contract for nunif_b200.
+
+Default workload (BASELINE.json configs[1]): waifu2x swin_unet/art scale4x, one synthetic 4K
+(3x2160x3840) frame per step through `tiled_render(tile_size=256, batch_size=16)` = 170 tiles,
+random-init weights (seed 0), fp16 tensor-core compute.  Metric = input megapixels / second.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's engine (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                      # the reference algorithm on the host CPU cores (oracle port)
+
+One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME = {"4k": (2160, 3840), "1080p": (1080, 1920), "8k": (4320, 7680)}
+TILE, BATCH = 256, 16
+SWIN4X_TILE_GFLOP = 155.7           # BASELINE.md section 2 (conv 8.6 + addmm 140.1 + bmm 7.0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mx = max(int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_sample(n_tiles, threads):
+    """The reference algorithm on the CPU (oracle port, fp32 like nunif/device.py:59-65 on CPU):
+    n_tiles 256x256 tiles of swin_unet_4x through model(minibatch).  Returns seconds."""
+    import torch
+    from nunif_b200 import synth
+    from oracle import swin_unet as osw
+    torch.set_num_threads(threads)
+    sd = synth.swin_unet_state_dict(0, 4)
+    x = torch.stack([synth.synth_image(100 + i, 3, TILE, TILE) for i in range(n_tiles)])
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        osw.swin_unet_forward(sd, x, 4)
+        return time.perf_counter() - t0
+
+
+def frame_tiles(h, w):
+    from oracle import seam_blending as osb
+    cfg = osb.create_config(h, w, 4, 32, TILE, 16)
+    return cfg["h_blocks"] * cfg["w_blocks"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    h, w = FRAME[args.frame]
+    ntiles = frame_tiles(h, w)
+    cores = host_cores()
+    sample_tiles = 2
+    mp_per_step = (h * w / 1e6) * sample_tiles / ntiles
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_sample(1, cores)
+    ts = [cpu_reference_sample(sample_tiles, cores) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    val = mp_per_step / t
+    line = {
+        "impl": "reference", "metric": "waifu2x_input_megapixels_per_sec", "value": val, "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} frame, tile_size=256 (CPU sample)"},
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_tiles} of the {ntiles} 256x256 tiles of one {args.frame} frame per step, "
+                                   f"oracle/swin_unet.py on torch-CPU fp32; MP/s = frame MP * {sample_tiles}/{ntiles} / t"},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from nunif_b200 import synth, _lib
+    from nunif_b200.nunif.models import create_model
+    from nunif_b200.nunif.render import tiled_render
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    _lib.check(lib.nb200_check_device(local))
+
+    h, w = FRAME[args.frame]
+    ntiles = frame_tiles(h, w)
+    # every rank builds the same container; rank 0's packed weight blob is broadcast once over NCCL
+    # (replaces torch.nn.parallel.replicate, nunif/models/data_parallel.py:16,58)
+    model = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), dev)
+    if world > 1:
+        ptr, nbytes = model.weight_blob()
+
+        class _Blob:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        blob = torch.as_tensor(_Blob(), device=dev)
+        dist.broadcast(blob, src=0)
+    # per-rank frame (weak scaling: one frame per GPU per step), already resident in HBM
+    x = synth.synth_image(1000 + rank, 3, h, w, smooth=False).to(dev)
+    x_host = synth.synth_image(1000 + rank, 3, h, w, smooth=False).pin_memory()
+    out_host = torch.empty((3, h * 4, w * 4), dtype=torch.float32).pin_memory()
+
+    def step():
+        return tiled_render(x, model, tile_size=TILE, batch_size=BATCH)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = step()
+        del y
+        barrier()
+        launches0 = lib.nb200_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            e0.record()
+            for _ in range(args.steps):
+                y = step()
+            e1.record()
+            barrier()
+        launches = lib.nb200_launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+        del y
+        # ---- end-to-end through the public API with host buffers (H2D + render + D2H every step)
+        e2e_steps = max(1, min(args.steps, 3))
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(e2e_steps):
+            xd = x_host.to(dev, non_blocking=True)
+            yd = tiled_render(xd, model, tile_size=TILE, batch_size=BATCH)
+            out_host.copy_(yd, non_blocking=True)
+            del yd
+        g1.record()
+        barrier()
+        ms_e2e = g0.elapsed_time(g1)
+        # ---- kernel-class timing for the roofline (one extra, untimed-for-`value` step)
+        _lib.check(lib.nb200_profile_enable(1))
+        y = step()
+        import ctypes
+        buf = ctypes.create_string_buffer(8192)
+        _lib.check(lib.nb200_profile_report(buf, 8192))
+        _lib.check(lib.nb200_profile_enable(0))
+        prof = json.loads(buf.value.decode())
+        del y
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    mp = h * w / 1e6
+    value = world * args.steps * mp / (ms / 1e3)
+    e2e = world * e2e_steps * mp / (ms_e2e / 1e3)
+    peaks, peak_src = load_peaks()
+    gemm = prof.get("gemm", {"launches": 0, "ms": 0.0, "work": 0.0})
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    ach = gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    line = {
+        "metric": "waifu2x_input_megapixels_per_sec", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} input 3x{h}x{w}, tile_size=256 batch=16, "
+                               f"{ntiles} tiles/frame, 1 frame/GPU/step",
+                   "parallelism": f"frame-parallel x{world} (no data-path collective; NCCL weight broadcast at load)",
+                   "weights": "random-init seed 0 (nunif_b200.synth)",
+                   "l2": "inputs/activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                   "frames_per_sec": world * args.steps / (ms / 1e3),
+                   "output_megapixels_per_sec": value * 16,
+                   "model_tflops_per_sec": world * args.steps * ntiles * SWIN4X_TILE_GFLOP / 1e3 / (ms / 1e3)},
+        "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": 3 * h * w * 4, "d2h_bytes_per_step": 3 * h * w * 16 * 4,
+                "steps": e2e_steps, "note": "pinned host input -> tiled_render -> pinned host output (reference default output_device='cpu')"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit GEMM, all shapes of one frame)",
+                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                     "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
+                     "launches": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
+                     "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None, "traffic": None},
+        "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            sample_tiles = 2
+            tcpu = cpu_reference_sample(sample_tiles, cores)
+            line["cpu_baseline"] = {
+                "value": mp * sample_tiles / ntiles / tcpu, "unit": "MP/s", "cores": cores, "kind": "port",
+                "sample": f"{sample_tiles} of {ntiles} tiles (256x256) of the same frame through oracle/swin_unet.py, torch-CPU fp32, "
+                          f"{tcpu:.2f} s; MP/s = frame MP * {sample_tiles}/{ntiles} / t"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frame", default="4k", choices=list(FRAME))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,8 @@
  *   - all pointers are DEVICE pointers unless the name ends in _host
  *   - images are planar float32 CHW / BCHW exactly as the reference passes them
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - divergence / convergence are doubles: the reference folds them into fp32 constants from
+ *     Python floats (e.g. float(shift_size * convergence)), and bit-exactness needs the same rounding
  *   - every function returns 0 on success, non-zero on error;
  *     nb200_last_error() returns a thread-local message
  *   - there is no CPU fallback: a call without a usable sm_100 device fails
@@ -120,7 +122,7 @@ enum { NB200_COMPOSE_NONE = 0,      /* separate left/right planar tensors       
  * compose NONE: left,right = [B][3][H][W]; SBS: left = [B][3][H][2W], right unused;
  * ANAGLYPH: left = [B][3][H][W], right unused. */
 int nb200_backward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
-                        float divergence, float convergence, int synthetic_view, int compose,
+                        double divergence, double convergence, int synthetic_view, int compose,
                         float* left, float* right, void* stream);
 
 /* iw3/forward_warp.py:246-256 apply_divergence_forward_warp (inconsistent_shift=False).
@@ -129,7 +131,7 @@ int nb200_backward_warp(const float* c, const float* depth, int B, int H, int W,
  * workspace: nb200_forward_warp_workspace() bytes (may be NULL if depth is full-res). */
 size_t nb200_forward_warp_workspace(int B, int H, int W, int h, int w);
 int nb200_forward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
-                       float divergence, float convergence, int fill, int synthetic_view,
+                       double divergence, double convergence, int fill, int synthetic_view,
                        int width_base, int compose, float* left, float* right,
                        float* left_mask, float* right_mask, void* workspace, void* stream);
 
@@ -175,6 +177,12 @@ int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci, int Cin, i
  * qkv [B][H][W][3C] fp16 -> out [B][H][W][C] fp16; bias_table fp32 [121][6]. */
 int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B,
                                int H, int W, int C, int heads, int shift, void* stream);
+
+/* Kernel-class device timing (CUDA events around every launch of this library) used by
+ * bench.py for the live roofline figure.  report writes a JSON object
+ * {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...} and synchronises the device. */
+int nb200_profile_enable(int on);
+int nb200_profile_report(char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

@@ -1,10 +1,40 @@
 // Library-wide state and the small utility entry points of the C ABI.
 #include "common.cuh"
+#include <cstring>
 #include "../../include/nunif_b200.h"
+
+#include <mutex>
+#include <vector>
 
 namespace nb200 {
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_prof_enabled{0};
+
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static const char* kCatNames[PC_COUNT] = {"gemm", "window_attention", "stem_conv", "to_image", "tile_unfold", "tile_blend",
+                                          "se_block", "tail_conv", "forward_warp", "backward_warp", "dilate_edge",
+                                          "minmax_map", "other"};
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(cudaStream_t st, int cat, double work) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r; r.a = prof_event(); r.b = prof_event(); r.cat = cat; r.work = work;
+    cudaEventRecord(r.a, st);
+    g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().b, st);
+}
 }  // namespace nb200
 
 using namespace nb200;
@@ -24,5 +54,41 @@ extern "C" int nb200_check_device(int device) {
     if (prop.major != 10)
         return fail(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                     "; this library is built for sm_100a (B200) only");
+    return 0;
+}
+
+// Kernel-class timing for bench.py: enable, run, then read a JSON object
+// {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...}.  Reading synchronises the device.
+extern "C" int nb200_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof_recs.clear();
+    g_prof_enabled.store(on ? 1 : 0);
+    return 0;
+}
+
+extern "C" int nb200_profile_report(char* buf, size_t cap) {
+    NB_CHECK(buf && cap > 0, "null buffer");
+    NB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double ms[PC_COUNT] = {0}, work[PC_COUNT] = {0};
+    long n[PC_COUNT] = {0};
+    for (auto& r : g_prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cat] += t; work[r.cat] += r.work; n[r.cat]++; }
+    }
+    std::string s = "{";
+    bool first = true;
+    for (int c = 0; c < PC_COUNT; ++c) {
+        if (!n[c]) continue;
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kCatNames[c], n[c],
+                 ms[c], work[c]);
+        s += tmp;
+        first = false;
+    }
+    s += "}";
+    NB_CHECK(s.size() + 1 <= cap, "buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
     return 0;
 }

@@ -38,6 +38,23 @@ inline int fail(const std::string& msg) {
             return ::nb200::fail(std::string(__func__) + ": launch -> " + cudaGetErrorString(_e)); \
     } while (0)
 
+// ---- optional in-library kernel timing (bench.py roofline): CUDA events around each launch
+enum ProfCat : int { PC_GEMM = 0, PC_ATTN, PC_STEM, PC_TOIMG, PC_UNFOLD, PC_BLEND, PC_SE, PC_TAIL, PC_WARP_FW, PC_WARP_BW,
+                     PC_DILATE, PC_MINMAX, PC_OTHER, PC_COUNT };
+extern std::atomic<int> g_prof_enabled;
+void prof_begin(cudaStream_t st, int cat, double work);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(cudaStream_t s, int cat, double work) : st(s), on(g_prof_enabled.load(std::memory_order_relaxed) != 0) {
+        if (on) prof_begin(st, cat, work);
+    }
+    ~ProfScope() {
+        if (on) prof_end(st);
+    }
+};
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

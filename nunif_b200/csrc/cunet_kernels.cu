@@ -55,21 +55,19 @@ __global__ void se_fc_kernel(const float* __restrict__ partial, int nchunks, int
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < nchunks; ++k) s += partial[((size_t)b * nchunks + k) * C + c];
-        mean[c] = __half2float(__float2half_rn(s / (float)HW));  // adaptive_avg_pool2d output is fp16 under autocast
+        mean[c] = s / (float)HW;
     }
     __syncthreads();
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         float s = b1[r];
         for (int c = 0; c < C; ++c) s += mean[c] * w1[r * C + c];
-        s = __half2float(__float2half_rn(s));
         hid[r] = fmaxf(s, 0.f);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = b2[c];
         for (int r = 0; r < R; ++r) s += hid[r] * w2[c * R + r];
-        s = __half2float(__float2half_rn(s));
-        scale[(size_t)b * C + c] = __half2float(__float2half_rn(1.f / (1.f + __expf(-s))));
+        scale[(size_t)b * C + c] = 1.f / (1.f + __expf(-s));
     }
 }
 
@@ -96,6 +94,7 @@ __global__ void __launch_bounds__(256) se_scale_kernel(__half* __restrict__ x, c
 int se_block(cudaStream_t st, __half* x, int n, int H, int W, int C, const float* w1, const float* b1, const float* w2,
              const float* b2, float* partial, float* scale) {
     const int HW = H * W, nchunks = cdiv(HW, SE_CHUNK);
+    ProfScope ps(st, PC_SE, (double)n * HW * C * 2 * 3);
     if (C == 64) {
         se_pool_partial_kernel<64><<<dim3(nchunks, n), 256, 0, st>>>(x, partial, HW, nchunks);
         NB_LAUNCHED();
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(128) tail_conv_kernel(const __half* __restrict
         __align__(16) __half o[8];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            float v = __half2float(__float2half_rn(acc[k]));
+            float v = acc[k];
             if (clip) v = clamp01(v);
             o[k] = __float2half_rn(v);
         }
@@ -198,7 +197,7 @@ __global__ void __launch_bounds__(128) tail_conv_kernel(const __half* __restrict
         const __half* zp = z1 + (((size_t)b * z1H + oy + 20) * z1W + ox + 20) * 8;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float v = __half2float(__float2half_rn(acc[k])) + __half2float(zp[k]);
+            const float v = acc[k] + __half2float(zp[k]);
             out[(((size_t)b * 3 + k) * Ho + oy) * Wo + ox] = __float2half_rn(clamp01(v));
         }
     }
@@ -209,6 +208,7 @@ int tail_conv(cudaStream_t st, int mode, int epi, const __half* x, const float* 
     const int Ho = mode == 0 ? Hi - 2 : 2 * Hi - 4, Wo = mode == 0 ? Wi - 2 : 2 * Wi - 4;
     const size_t total = (size_t)n * Ho * Wo;
     const unsigned blocks = (unsigned)cdiv64(total, 128);
+    ProfScope ps(st, PC_TAIL, (double)n * Hi * Wi * 128 + (double)total * 16);
     if (mode == 0 && epi == 0) tail_conv_kernel<0, 0><<<blocks, 128, 0, st>>>(x, wt, bias, out, z1, n, Hi, Wi, Ho, Wo, z1H, z1W, clip);
     else if (mode == 0 && epi == 1) tail_conv_kernel<0, 1><<<blocks, 128, 0, st>>>(x, wt, bias, out, z1, n, Hi, Wi, Ho, Wo, z1H, z1W, clip);
     else if (mode == 1 && epi == 0) tail_conv_kernel<1, 0><<<blocks, 128, 0, st>>>(x, wt, bias, out, z1, n, Hi, Wi, Ho, Wo, z1H, z1W, clip);

@@ -232,6 +232,7 @@ extern "C" int nb200_dilate_edge(const float* x, int B, int h, int w, int x_iter
         // choose destinations so the last iteration lands in `out` and never aliases src
         float* dst = ((total - 1 - it) % 2 == 0) ? out : ping;
         if (dst == src) dst = (dst == out) ? ping : out;
+        ProfScope ps(st, PC_DILATE, (double)n * 4 * 2);
         range_stats_kernel<<<dim3(nblk, B), DL_THREADS, 0, st>>>(src, range, partials, h, w);
         NB_LAUNCHED();
         range_finalize_kernel<<<B, 32, 0, st>>>(partials, nblk, h * w, stats);
@@ -251,6 +252,7 @@ extern "C" int nb200_minmax_map(const float* depth, int B, int n_per_frame, floa
     const int nblk = dl_blocks(n_per_frame);
     float2* partials = nullptr;
     NB_CUDA(cudaMallocAsync((void**)&partials, (size_t)B * nblk * sizeof(float2), st));
+    ProfScope ps(st, PC_MINMAX, (double)B * n_per_frame * 4 * 3);
     minmax_partial_kernel<<<dim3(nblk, B), DL_THREADS, 0, st>>>(depth, partials, n_per_frame);
     NB_LAUNCHED();
     minmax_apply_kernel<<<dim3(nblk, B), DL_THREADS, 0, st>>>(depth, partials, nblk, n_per_frame, mapper_c, out, minmax_out);

@@ -144,6 +144,7 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     cuuint32_t bbox[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
     if (encode(&tb, g.Wt, 2, bdims, bstr, bbox, BK * 2)) return 1;
     const int m_tiles = p.tiles_x * p.tiles_y * p.B, n_tiles = g.N / bn;
+    ProfScope ps(st, PC_GEMM, 2.0 * (double)p.B * p.Ho * p.Wo * (double)g.N * (double)K);
     return BK == 64 ? launch_bn<64>(bn, st, ta, tb, p, m_tiles, n_tiles) : launch_bn<32>(bn, st, ta, tb, p, m_tiles, n_tiles);
 }
 

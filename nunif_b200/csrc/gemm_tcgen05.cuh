@@ -287,15 +287,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
             for (int j = 0; j < 8; ++j) {
                 float a0 = v[2 * j], a1 = v[2 * j + 1];
                 if (rs && p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
-                if (p.act != ACT_NONE) {
-                    // the reference applies the activation to the fp16 Linear/Conv output (autocast)
-                    a0 = apply_act(__half2float(__float2half_rn(a0)), p.act);
-                    a1 = apply_act(__half2float(__float2half_rn(a1)), p.act);
-                }
+                a0 = apply_act(a0, p.act);
+                a1 = apply_act(a1, p.act);
                 if (rs && !p.res_before_act) {
-                    // the reference adds two fp16 tensors: round the branch output first
-                    a0 = __half2float(__float2half_rn(a0)) + rv[2 * j];
-                    a1 = __half2float(__float2half_rn(a1)) + rv[2 * j + 1];
+                    a0 += rv[2 * j];
+                    a1 += rv[2 * j + 1];
                 }
                 o[j] = __floats2half2_rn(a0, a1);
             }

@@ -121,6 +121,7 @@ extern "C" int nb200_tile_unfold(const float* x, int C, int H, int W, const nb20
     NB_CHECK(C <= cpad, "cpad must be >= C");
     NB_CHECK(tile0 >= 0 && n > 0 && tile0 + n <= cfg->h_blocks * cfg->w_blocks, "tile range out of bounds");
     const size_t total = (size_t)n * tile_size * tile_size;
+    ProfScope ps((cudaStream_t)stream, PC_UNFOLD, (double)total * (C * 4 + cpad * 2));
     tile_unfold_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(
         x, C, H, W, cfg->pad_l, cfg->pad_t, cfg->w_blocks, cfg->input_tile_step, tile_size, tile0, n, cpad, (__half*)dst);
     NB_LAUNCHED();
@@ -145,6 +146,7 @@ extern "C" int nb200_tile_gather_blend(const void* z_all, int C, const nb200_til
         const int i = blend_size - 1 - d;
         p.ring[d] = (float)(1.0 - (1.0 / (blend_size + 1)) * (i + 1));
     }
+    ProfScope ps((cudaStream_t)stream, PC_BLEND, (double)C * p.y_h * p.y_w * 4 + (double)p.h_blocks * p.w_blocks * C * p.S * p.S * 2);
     tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
     NB_LAUNCHED();
     return 0;

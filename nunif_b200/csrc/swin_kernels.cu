@@ -71,6 +71,7 @@ int stem_conv3x3(cudaStream_t st, const __half* x, const float* wt, const float*
     NB_CHECK(ldo >= cout_pad && ldo % 8 == 0, "bad output stride");
     const size_t total = (size_t)n * (Hi - 2) * (Wi - 2);
     const unsigned blocks = (unsigned)cdiv64(total, 128);
+    ProfScope ps(st, PC_STEM, (double)n * Hi * Wi * 16 + (double)total * ldo * 2);
     if (cout_pad == 64) stem_conv3x3_kernel<64><<<blocks, 128, 0, st>>>(x, wt, bias, out, n, Hi, Wi, ldo);
     else if (cout_pad == 32) stem_conv3x3_kernel<32><<<blocks, 128, 0, st>>>(x, wt, bias, out, n, Hi, Wi, ldo);
     else return fail("stem_conv3x3: unsupported channel count");
@@ -132,9 +133,8 @@ __global__ void __launch_bounds__(224) window_attention_kernel(const __half* __r
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 f = __half22float2(h[k]);
-                // q * scale is an fp16 tensor op in the reference (autocast): round like it does
-                qv[j + 2 * k] = __half2float(__float2half_rn(f.x * scale));
-                qv[j + 2 * k + 1] = __half2float(__float2half_rn(f.y * scale));
+                qv[j + 2 * k] = f.x * scale;
+                qv[j + 2 * k + 1] = f.y * scale;
             }
         }
     }
@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(224) window_attention_kernel(const __half* __r
                 acc += qv[j + 2 * e] * f.x + qv[j + 2 * e + 1] * f.y;
             }
         }
-        acc = __half2float(__float2half_rn(acc));  // fp16 matmul output (:188)
         const int ky = k / WS, kx = k - ky * WS;
         acc += stab[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head];  // :49-59,:190
         if (sreg[k] != qreg) acc += -100.0f;                                                    // :204-209
@@ -174,7 +173,7 @@ __global__ void __launch_bounds__(224) window_attention_kernel(const __half* __r
     for (int j = 0; j < D; ++j) o[j] = 0.f;
 #pragma unroll
     for (int k = 0; k < WTOK; ++k) {
-        const float pk = __half2float(__float2half_rn(s[k] * inv));  // softmax output cast to fp16 for the PV matmul (:214)
+        const float pk = s[k] * inv;
         const __half* vp = sv + k * C + head * D;
 #pragma unroll
         for (int j = 0; j < D; j += 8) {
@@ -204,6 +203,7 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table
     NB_CHECK(C == 96 || C == 192, "window attention supports C=96 (d=16) and C=192 (d=32)");
     if (WS >= H) shift = 0;  // torchvision :151-155
     dim3 grid((H / WS) * (W / WS), B);
+    ProfScope ps(st, PC_ATTN, (double)B * H * W * C * 4 * 2);  // bytes: read q,k,v + write out
     if (C == 96) window_attention_kernel<16><<<grid, 224, 0, st>>>(qkv, bias_table, out, H, W, shift);
     else window_attention_kernel<32><<<grid, 224, 0, st>>>(qkv, bias_table, out, H, W, shift);
     NB_LAUNCHED();
@@ -262,6 +262,7 @@ int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws,
     NB_CHECK(down == 1 || down == 2 || down == 4, "downscale must be 1, 2 or 4");
     NB_CHECK(Hs == Ws && (Hs * r) % down == 0, "bad ToImage geometry");
     const size_t total = (size_t)n * 3 * (Hs * r / down) * (Ws * r / down);
+    ProfScope ps(st, PC_TOIMG, (double)n * Hs * Ws * cs * 2 + (double)total * 2);
     to_image_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(y, z, n, Hs, Ws, cs, r, down);
     NB_LAUNCHED();
     return 0;

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) anaglyph_dubois_kernel(const float* __res
 using namespace nb200;
 
 extern "C" int nb200_backward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
-                                   float divergence, float convergence, int synthetic_view, int compose,
+                                   double divergence, double convergence, int synthetic_view, int compose,
                                    float* left, float* right, void* stream) {
     NB_CHECK(c && depth && left, "null pointer");
     NB_CHECK(compose != NB200_COMPOSE_NONE || right, "right output required for compose=NONE");
@@ -214,7 +214,7 @@ extern "C" int nb200_backward_warp(const float* c, const float* depth, int B, in
     if (synthetic_view != NB200_VIEW_BOTH) div = div * 2;           // backward_warp.py:101-102
     double shift = div * 0.01;                                       // :105
     p.shift = (float)shift;
-    p.shift_conv = (float)(shift * (double)convergence);             // :106
+    p.shift_conv = (float)(shift * convergence);             // :106
     p.delta_scale = (float)((double)(h > w ? h : w) / (double)w);    // :108
     p.sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
     p.sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
@@ -224,6 +224,8 @@ extern "C" int nb200_backward_warp(const float* c, const float* depth, int B, in
     constexpr int VEC = 4;
     dim3 block(256), grid(cdiv(cdiv(W, VEC), 256), H, B);
     cudaStream_t st = (cudaStream_t)stream;
+    // algorithmic bytes: 3 planes in + output planes + the depth map
+    ProfScope ps(st, PC_WARP_BW, (double)B * H * W * 4 * (3 + (compose == NB200_COMPOSE_ANAGLYPH_DUBOIS ? 3 : 6)) + (double)B * h * w * 4);
     switch (compose) {
         case NB200_COMPOSE_NONE: backward_warp_kernel<NB200_COMPOSE_NONE, VEC><<<grid, block, 0, st>>>(p); break;
         case NB200_COMPOSE_SBS: backward_warp_kernel<NB200_COMPOSE_SBS, VEC><<<grid, block, 0, st>>>(p); break;

@@ -304,7 +304,7 @@ extern "C" size_t nb200_forward_warp_workspace(int B, int H, int W, int h, int w
 }
 
 extern "C" int nb200_forward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
-                                  float divergence, float convergence, int fill, int synthetic_view,
+                                  double divergence, double convergence, int fill, int synthetic_view,
                                   int width_base, int compose, float* left, float* right,
                                   float* left_mask, float* right_mask, void* workspace, void* stream) {
     (void)workspace;
@@ -322,7 +322,7 @@ extern "C" int nb200_forward_warp(const float* c, const float* depth, int B, int
     p.Wp = W + 2 * p.P;
     const double shift_size = div * 0.01 * base * 0.5;               // :166
     p.shift_size = (float)shift_size;
-    p.conv_term = (float)(shift_size * (double)convergence);         // :167
+    p.conv_term = (float)(shift_size * convergence);         // :167
     p.fill = fill;
     p.do_left = synthetic_view != NB200_VIEW_RIGHT;
     p.do_right = synthetic_view != NB200_VIEW_LEFT;
@@ -333,7 +333,10 @@ extern "C" int nb200_forward_warp(const float* c, const float* depth, int B, int
     NB_CHECK(smem <= 227 * 1024, "row (with divergence padding) does not fit shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     NB_CUDA(cudaFuncSetAttribute(forward_warp_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    forward_warp_row_kernel<<<dim3(H, B), FW_THREADS, smem, st>>>(p);
+    {
+        ProfScope ps(st, PC_WARP_FW, (double)B * H * W * 4 * 9 + (double)B * h * w * 4);
+        forward_warp_row_kernel<<<dim3(H, B), FW_THREADS, smem, st>>>(p);
+    }
     NB_LAUNCHED();
     if (synthetic_view != NB200_VIEW_BOTH) {
         // the non-synthesised eye is the source image
