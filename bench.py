@@ -121,7 +121,8 @@ def run_reference(args):
         "impl": "reference", "metric": "waifu2x_input_megapixels_per_sec", "value": val, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} frame, tile_size=256 (CPU sample)"},
+        "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} input 3x{h}x{w}, tile_size=256 batch=16, "
+                               f"{ntiles} tiles/frame, 1 frame/GPU/step"},
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port",
                          "sample": f"{sample_tiles} of the {ntiles} 256x256 tiles of one {args.frame} frame per step, "
                                    f"oracle/swin_unet.py on torch-CPU fp32; MP/s = frame MP * {sample_tiles}/{ntiles} / t"},
@@ -154,12 +155,8 @@ def run_b200(args):
     # (replaces torch.nn.parallel.replicate, nunif/models/data_parallel.py:16,58)
     model = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), dev)
     if world > 1:
-        ptr, nbytes = model.weight_blob()
-
-        class _Blob:
-            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-        blob = torch.as_tensor(_Blob(), device=dev)
-        dist.broadcast(blob, src=0)
+        from nunif_b200 import parallel
+        parallel.broadcast_model_weights(model, src=0)
     # per-rank frame (weak scaling: one frame per GPU per step), already resident in HBM
     x = synth.synth_image(1000 + rank, 3, h, w, smooth=False).to(dev)
     x_host = synth.synth_image(1000 + rank, 3, h, w, smooth=False).pin_memory()

@@ -39,29 +39,29 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 }
 
 template <int BN, int BK>
-static int launch_t(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int m_tiles, int n_tiles) {
+static int launch_t(cudaStream_t st, const GemmMaps& maps, const GemmParams& p, int m_tiles, int n_tiles) {
     using Cfg = GemmCfg<BN, BK>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         NB_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    gemm_conv_kernel<BN, BK><<<dim3(m_tiles, n_tiles), GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+    gemm_conv_kernel<BN, BK><<<dim3((unsigned)m_tiles * n_tiles), GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
     NB_LAUNCHED();
     return 0;
 }
 
 template <int BK>
-static int launch_bn(int bn, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int m_tiles, int n_tiles) {
+static int launch_bn(int bn, cudaStream_t st, const GemmMaps& maps, const GemmParams& p, int m_tiles, int n_tiles) {
     switch (bn) {
-        case 16: return launch_t<16, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 32: return launch_t<32, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 48: return launch_t<48, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 64: return launch_t<64, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 96: return launch_t<96, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 128: return launch_t<128, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 192: return launch_t<192, BK>(st, ta, tb, p, m_tiles, n_tiles);
-        case 256: return launch_t<256, BK>(st, ta, tb, p, m_tiles, n_tiles);
+        case 16: return launch_t<16, BK>(st, maps, p, m_tiles, n_tiles);
+        case 32: return launch_t<32, BK>(st, maps, p, m_tiles, n_tiles);
+        case 48: return launch_t<48, BK>(st, maps, p, m_tiles, n_tiles);
+        case 64: return launch_t<64, BK>(st, maps, p, m_tiles, n_tiles);
+        case 96: return launch_t<96, BK>(st, maps, p, m_tiles, n_tiles);
+        case 128: return launch_t<128, BK>(st, maps, p, m_tiles, n_tiles);
+        case 192: return launch_t<192, BK>(st, maps, p, m_tiles, n_tiles);
+        case 256: return launch_t<256, BK>(st, maps, p, m_tiles, n_tiles);
     }
     return fail("unsupported BLOCK_N");
 }
@@ -71,6 +71,15 @@ int pick_block_n(int N) {
     for (int c : cands)
         if (N % c == 0) return c;
     return 0;
+}
+
+// 4-D NHWC view (c, x, y, b) of an fp16 tensor for the epilogue's TMA stores / residual loads
+static int encode_nhwc4(CUtensorMap* m, const __half* base, int C, int X, int Y, int B, long long sx, long long sy, long long sb,
+                        int cw, int tw, int th) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sb * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    return encode(m, base, 4, dims, strides, box, cw * 2);
 }
 
 int conv_gemm(cudaStream_t st, const ConvGemm& g) {
@@ -124,28 +133,59 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     p.tiles_x = cdiv(p.Wo, p.TW);
     p.tiles_y = cdiv(p.Ho, p.TH);
     p.N = g.N;
-    p.bias = g.bias; p.act = g.act; p.out = g.out; p.ldo = g.ldo; p.out_mode = g.out_mode; p.cout = g.cout;
-    p.res = g.res; p.ldr = g.ldr; p.res_H = g.res_H; p.res_W = g.res_W; p.res_cy = g.res_cy; p.res_cx = g.res_cx;
+    p.bias = g.bias; p.act = g.act; p.out_mode = g.out_mode; p.cout = g.cout;
+    p.has_res = g.res ? 1 : 0;
     p.res_before_act = g.res_before_act;
-    if (g.kind == CG_LINEAR_FLAT && g.res) { p.res_H = 1; p.res_W = p.Wo; p.res_cy = p.res_cx = 0; }
-    if (g.out_mode == OUT_PIXSHUF2) {
+    const bool shuf = g.out_mode == OUT_PIXSHUF2;
+    if (shuf) {
         NB_CHECK(g.kind != CG_LINEAR_FLAT, "pixel-shuffle output needs 2-D tiling");
         NB_CHECK(g.cout % 16 == 0 && g.N == 4 * g.cout, "pixel-shuffle: N must be 4*cout, cout % 16 == 0");
     }
     NB_CHECK(g.ldo % 8 == 0 && (!g.res || g.ldr % 8 == 0), "channel strides must be multiples of 8");
     const int bn = pick_block_n(g.N);
     NB_CHECK(bn > 0, "no BLOCK_N divides N");
+    const int cw = (bn % 64 == 0) ? 64 : ((bn % 32 == 0) ? 32 : 16);
+    NB_CHECK(!shuf || g.cout % cw == 0, "pixel-shuffle: cout must be a multiple of the store chunk");
+    p.n_tiles = g.N / bn;
     box[0] = BK; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
-    CUtensorMap ta, tb;
-    if (encode(&ta, g.A, 5, dims, strides, box, BK * 2)) return 1;
+    GemmMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (encode(&maps.a, g.A, 5, dims, strides, box, BK * 2)) return 1;
     const int K = p.taps * ktap;
     cuuint64_t bdims[2] = {(cuuint64_t)K, (cuuint64_t)g.N};
     cuuint64_t bstr[1] = {(cuuint64_t)K * e};
     cuuint32_t bbox[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
-    if (encode(&tb, g.Wt, 2, bdims, bstr, bbox, BK * 2)) return 1;
-    const int m_tiles = p.tiles_x * p.tiles_y * p.B, n_tiles = g.N / bn;
+    if (encode(&maps.b, g.Wt, 2, bdims, bstr, bbox, BK * 2)) return 1;
+    // ---- output / residual views
+    if (!shuf) {
+        if (encode_nhwc4(&maps.o[0], g.out, g.N, p.Wo, p.Ho, p.B, g.ldo, (long long)p.Wo * g.ldo, (long long)p.Ho * p.Wo * g.ldo,
+                         cw, p.TW, p.TH)) return 1;
+        if (g.res) {
+            const int rW = g.kind == CG_LINEAR_FLAT ? p.Wo : g.res_W, rH = g.kind == CG_LINEAR_FLAT ? 1 : g.res_H;
+            p.res_cx = g.kind == CG_LINEAR_FLAT ? 0 : g.res_cx;
+            p.res_cy = g.kind == CG_LINEAR_FLAT ? 0 : g.res_cy;
+            if (encode_nhwc4(&maps.r[0], g.res, g.N, rW, rH, p.B, g.ldr, (long long)rW * g.ldr, (long long)rH * rW * g.ldr, cw,
+                             p.TW, p.TH)) return 1;
+        }
+    } else {
+        const int OW = 2 * p.Wo, OH = 2 * p.Ho;
+        for (int q = 0; q < 4; ++q) {
+            const int dy = q >> 1, dx = q & 1;
+            if (encode_nhwc4(&maps.o[q], g.out + ((size_t)dy * OW + dx) * g.ldo, g.cout, p.Wo, p.Ho, p.B, 2LL * g.ldo,
+                             2LL * OW * g.ldo, (long long)OH * OW * g.ldo, cw, p.TW, p.TH)) return 1;
+            if (g.res) {
+                // crop folded into the base: position (2y+dy+cy, 2x+dx+cx) of the residual tensor
+                const int oy = dy + g.res_cy, ox = dx + g.res_cx;
+                NB_CHECK(oy + 2 * (p.Ho - 1) < g.res_H && ox + 2 * (p.Wo - 1) < g.res_W, "residual tensor too small");
+                if (encode_nhwc4(&maps.r[q], g.res + ((size_t)oy * g.res_W + ox) * g.ldr, g.cout, p.Wo, p.Ho, p.B, 2LL * g.ldr,
+                                 2LL * g.res_W * g.ldr, (long long)g.res_H * g.res_W * g.ldr, cw, p.TW, p.TH)) return 1;
+            }
+        }
+        p.res_cx = p.res_cy = 0;
+    }
+    const int m_tiles = p.tiles_x * p.tiles_y * p.B;
     ProfScope ps(st, PC_GEMM, 2.0 * (double)p.B * p.Ho * p.Wo * (double)g.N * (double)K);
-    return BK == 64 ? launch_bn<64>(bn, st, ta, tb, p, m_tiles, n_tiles) : launch_bn<32>(bn, st, ta, tb, p, m_tiles, n_tiles);
+    return BK == 64 ? launch_bn<64>(bn, st, maps, p, m_tiles, p.n_tiles) : launch_bn<32>(bn, st, maps, p, m_tiles, p.n_tiles);
 }
 
 }  // namespace nb200

@@ -13,7 +13,9 @@
 //              128B/64B hardware swizzle, mbarrier complete_tx
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 per instr),
 //              tcgen05.commit releases smem stages and finally signals the epilogue
-//   warps 2-5: epilogue - tcgen05.ld accumulator rows, bias + activation (+ residual), fp16 NHWC store
+//   warps 2-5: epilogue - tcgen05.ld accumulator rows, bias + activation (+ residual tile fetched by TMA),
+//              fp16 results staged in 128B-swizzled shared memory and written with TMA tensor stores
+//              (cp.async.bulk.tensor ... bulk_group), so every global access of the kernel is a full-line bulk copy
 // Non-persistent, one 128 x BLOCK_N output tile per CTA; shared memory is sized so that two CTAs
 // are co-resident per SM, which overlaps one tile's epilogue with the next tile's loads.
 #pragma once
@@ -31,15 +33,20 @@ struct GemmParams {
     int N;               // output channels (GEMM N)
     int taps, cpt;       // taps and BK-chunks per tap (K = taps*cpt*BK)
     int8_t tap_dx[16], tap_dy[16], tap_dyi[16];
-    // epilogue
+    int n_tiles;
+    // epilogue (output / residual tensors are described by the tensor maps in GemmMaps)
     const float* bias;   // [N] or null
     int act;
-    __half* out;         // NHWC fp16
-    int ldo;             // channel stride (elements per pixel) of out
-    int out_mode, cout;  // OUT_PIXSHUF2: N = 4*cout, out is [B][2Ho][2Wo][ldo]
-    const __half* res;   // optional residual, NHWC [B][res_H][res_W][ldr], read at (y+res_cy, x+res_cx)
-    int ldr, res_H, res_W, res_cy, res_cx;
+    int out_mode, cout;  // OUT_PIXSHUF2: N = 4*cout ordered (dy,dx,co); maps o[g]/r[g] are the stride-2 views
+    int has_res, res_cy, res_cx;
     int res_before_act;  // 0: out = act(acc+bias) + res ; 1: out = act(acc+bias+res)
+};
+
+// All tensor maps of one launch (a single __grid_constant__ parameter).
+struct GemmMaps {
+    CUtensorMap a, b;
+    CUtensorMap o[4];    // output: NHWC view (c, x, y, b); pixel-shuffle mode: one stride-2 view per (dy,dx)
+    CUtensorMap r[4];    // residual, same tiling as the output
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -82,6 +89,19 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -156,40 +176,58 @@ struct GemmCfg {
     static constexpr int B_BYTES = BLOCK_N * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
     static constexpr int STAGES = (98304 / STAGE_BYTES) < 2 ? 2 : ((98304 / STAGE_BYTES) > 6 ? 6 : (98304 / STAGE_BYTES));
+    // epilogue staging: BLOCK_N/CW chunks of [128 rows][CW cols] fp16, swizzle span = CW*2 bytes
+    static constexpr int CW = (BLOCK_N % 64 == 0) ? 64 : ((BLOCK_N % 32 == 0) ? 32 : 16);
+    static constexpr int NCH = BLOCK_N / CW;
+    static constexpr int CH_BYTES = 128 * CW * 2;
+    static_assert(NCH * CH_BYTES <= STAGES * STAGE_BYTES, "epilogue staging must fit in the (drained) pipeline stages");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : (BLOCK_N <= 64 ? 64 : (BLOCK_N <= 128 ? 128 : 256));
 };
 
+// byte offset of 16-byte chunk j of row r inside a [128][CW] staging tile with the TMA swizzle of span CW*2
+template <int CW>
+__device__ __forceinline__ uint32_t stage_off(int r, int j) {
+    if (CW == 64) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+    if (CW == 32) return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+    return (uint32_t)(r * 32 + ((j ^ ((r >> 2) & 1)) << 4));
+}
+
 template <int BLOCK_N, int BK>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_constant__ GemmMaps maps,
                                                                  const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, BK>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int CW = Cfg::CW;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* res_bar = tmem_full_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
+    // n tile is the fast grid index so CTAs sharing an A tile run together (A re-reads hit L2)
+    const int n_tile = blockIdx.x % p.n_tiles;
+    const int tile = blockIdx.x / p.n_tiles;
     const int tx_i = tile % p.tiles_x;
     const int ty_i = (tile / p.tiles_x) % p.tiles_y;
     const int b = tile / (p.tiles_x * p.tiles_y);
     const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
-    const int n0 = blockIdx.y * BLOCK_N;
+    const int n0 = n_tile * BLOCK_N;
     const int k_iters = p.taps * p.cpt;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&maps.a);
+        tma_prefetch_desc(&maps.b);
+        tma_prefetch_desc(&maps.o[0]);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        mbar_init(res_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -209,8 +247,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
                 uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                 uint8_t* sb = sa + Cfg::A_BYTES;
                 mbar_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::B_BYTES);
-                tma_load_5d(&tmA, &full_bar[s], sa, ch * BK, x0 + p.tap_dx[tap], p.tap_dyi[tap], y0 + p.tap_dy[tap], b);
-                tma_load_2d(&tmB, &full_bar[s], sb, it * BK, n0);
+                tma_load_5d(&maps.a, &full_bar[s], sa, ch * BK, x0 + p.tap_dx[tap], p.tap_dyi[tap], y0 + p.tap_dy[tap], b);
+                tma_load_2d(&maps.b, &full_bar[s], sb, it * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -237,67 +275,86 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
-        const int r = lane_grp * 32 + lane;       // accumulator row == pixel within the tile
-        const int ty = r / p.TW, tx = r - ty * p.TW;
-        const int y = y0 + ty, x = x0 + tx;
-        const bool valid = (y < p.Ho) && (x < p.Wo);
-        mbar_wait(tmem_full_bar, 0);
+        const int lane_grp = warp & 3;       // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+        const int r = lane_grp * 32 + lane;  // accumulator row == pixel within the tile == staging row
+        const bool leader = (warp == 2 && lane == 0);
+        mbar_wait(tmem_full_bar, 0);         // all MMAs retired => every pipeline stage is drained and reusable
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        const size_t pix = ((size_t)b * p.Ho + y) * p.Wo + x;
-        const __half* res_row = nullptr;
-        if (p.res && valid)
-            res_row = p.res + (((size_t)b * p.res_H + (y + p.res_cy)) * p.res_W + (x + p.res_cx)) * p.ldr;
+        uint8_t* stg = smem;
+        if (p.has_res) {
+            if (leader) {
+                mbar_expect_tx(res_bar, Cfg::NCH * Cfg::CH_BYTES);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-            uint32_t acc[16];
-            tmem_ld16(trow + c0, acc);
-            tmem_ld_wait();
-            const int n = n0 + c0;
-            if (!valid || n >= p.N) continue;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-            __half* dst;
-            const __half* rs = nullptr;
-            if (p.out_mode == OUT_PIXSHUF2) {
-                const int g = n / p.cout, co = n - g * p.cout;  // g = dy*2+dx
-                const size_t opix = ((size_t)b * (2 * p.Ho) + (2 * y + (g >> 1))) * (2 * p.Wo) + (2 * x + (g & 1));
-                dst = p.out + opix * p.ldo + co;
-                if (p.res) rs = p.res + (((size_t)b * p.res_H + (2 * y + (g >> 1) + p.res_cy)) * p.res_W + (2 * x + (g & 1) + p.res_cx)) * p.ldr + co;
-            } else {
-                dst = p.out + pix * p.ldo + n;
-                if (res_row) rs = res_row + n;
-            }
-            float rv[16];
-            if (rs) {
-                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rs));
-                const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rs) + 1);
-                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2 a = __half22float2(h0[j]), c = __half22float2(h1[j]);
-                    rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = c.x; rv[8 + 2 * j + 1] = c.y;
+                for (int c = 0; c < Cfg::NCH; ++c) {
+                    const int n = n0 + c * CW;
+                    const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
+                    const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
+                    tma_load_4d(&maps.r[g], res_bar, stg + c * Cfg::CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
                 }
             }
-            __align__(16) __half2 o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float a0 = v[2 * j], a1 = v[2 * j + 1];
-                if (rs && p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
-                a0 = apply_act(a0, p.act);
-                a1 = apply_act(a1, p.act);
-                if (rs && !p.res_before_act) {
-                    a0 += rv[2 * j];
-                    a1 += rv[2 * j + 1];
-                }
-                o[j] = __floats2half2_rn(a0, a1);
-            }
-            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(o)[0];
-            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(o)[1];
+            mbar_wait(res_bar, 0);
         }
+        const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < Cfg::NCH; ++c) {
+            uint8_t* buf = stg + c * Cfg::CH_BYTES;
+#pragma unroll
+            for (int sub = 0; sub < CW / 16; ++sub) {
+                uint32_t acc[16];
+                tmem_ld16(trow + c * CW + sub * 16, acc);
+                tmem_ld_wait();
+                const int n = n0 + c * CW + sub * 16;
+                float v[16];
+                if (p.bias) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
+                        v[4 * q] = __uint_as_float(acc[4 * q]) + bq.x;
+                        v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + bq.y;
+                        v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + bq.z;
+                        v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + bq.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+                }
+                uint4* s0 = reinterpret_cast<uint4*>(buf + stage_off<CW>(r, 2 * sub));
+                uint4* s1 = reinterpret_cast<uint4*>(buf + stage_off<CW>(r, 2 * sub + 1));
+                float rv[16];
+                if (p.has_res) {
+                    const uint4 r0 = *s0, r1 = *s1;
+                    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = __half22float2(h0[j]), d = __half22float2(h1[j]);
+                        rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = d.x; rv[8 + 2 * j + 1] = d.y;
+                    }
+                }
+                __align__(16) __half2 o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a0 = v[2 * j], a1 = v[2 * j + 1];
+                    if (p.has_res && p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
+                    a0 = apply_act(a0, p.act);
+                    a1 = apply_act(a1, p.act);
+                    if (p.has_res && !p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
+                    o[j] = __floats2half2_rn(a0, a1);
+                }
+                *s0 = reinterpret_cast<const uint4*>(o)[0];
+                *s1 = reinterpret_cast<const uint4*>(o)[1];
+            }
+            fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            epi_bar_sync();
+            if (leader) {
+                const int n = n0 + c * CW;
+                const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
+                const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
+                tma_store_4d(&maps.o[g], buf, co, x0, y0, b);  // out-of-range rows/cols of edge tiles are clipped by TMA
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_read();  // smem must stay valid until the bulk stores have read it
         tc_fence_before();
     }
     __syncthreads();

@@ -1,0 +1,234 @@
+// Shifted-window attention core on tensor cores (mma.sync m16n8k16, fp16 in / fp32 accumulate).
+//
+// One CTA per 6x6 window, one warp per head (6 warps).  The 36 tokens are padded to 48 rows:
+//   S = (Q*scale) K^T : M=48 (3 m16 tiles), N=48 (6 n8 tiles), K=d (d/16 steps)
+//   softmax on the accumulator fragments (quad shuffles), relative-position bias and the
+//   shift mask added per element, padded keys masked out
+//   O = P V           : the S fragments are re-packed in registers as the A operand (no smem trip),
+//                       V fragments come from ldmatrix.trans
+// torchvision swin_transformer.py:166-221 (roll, partition, bias :190, mask :193-209, softmax :211,
+// attn@v :214, un-roll) - everything but the qkv / proj Linears, which run on the tcgen05 GEMM.
+//
+// The 36x36 problem per head is far too small for a tcgen05 tile (M=128), and the op moves
+// 8*C bytes/token for ~144*C FLOP/token: it is HBM/L2-bound, so the warp-level HMMA path is the
+// right instrument here.
+#include "common.cuh"
+#include "swin_kernels.h"
+
+namespace nb200 {
+
+namespace {
+constexpr int WS = 6, WTOK = 36, WPAD = 48, HEADS = 6;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+}  // namespace
+
+template <int D>
+__global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias_table,
+                                                                   __half* __restrict__ out, int H, int W, int shift) {
+    constexpr int C = D * HEADS;
+    constexpr int LD = C + 8;  // padded row: (C+8)*2 bytes = 4 words mod 32 banks -> conflict-free fragment loads
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* sq = reinterpret_cast<__half*>(smem_raw);  // [WPAD][LD]  (q*scale), later the output tile
+    __half* sk = sq + WPAD * LD;
+    __half* sv = sk + WPAD * LD;
+    float* stab = reinterpret_cast<float*>(sv + WPAD * LD);  // [121][HEADS]
+    int* stok = reinterpret_cast<int*>(stab + 121 * HEADS);  // [WTOK]
+    int* sreg = stok + WTOK;                                 // [WPAD]
+    const int nww = W / WS;
+    const int wx = blockIdx.x % nww, wy = blockIdx.x / nww, b = blockIdx.y;
+    const int tid = threadIdx.x;
+    if (tid < WPAD) {
+        int reg = -1;
+        if (tid < WTOK) {
+            const int ry = wy * WS + tid / WS, rx = wx * WS + tid % WS;  // rolled coordinates
+            const int y = (ry + shift) % H, x = (rx + shift) % W;        // torch.roll(-shift) :166-167
+            stok[tid] = (b * H + y) * W + x;
+            int hr = 0, wr = 0;
+            if (shift > 0) {
+                hr = ry < H - WS ? 0 : (ry < H - shift ? 1 : 2);
+                wr = rx < W - WS ? 0 : (rx < W - shift ? 1 : 2);
+            }
+            reg = hr * 3 + wr;
+        }
+        sreg[tid] = reg;
+    }
+    for (int i = tid; i < 121 * HEADS; i += blockDim.x) stab[i] = bias_table[i];
+    __syncthreads();
+    // ---- stage q*scale, k, v (16-byte vectors; one token row = 3C contiguous halves in global)
+    constexpr int VPT = C / 8;
+    const __half2 scale2 = __float2half2_rn(D == 16 ? 0.25f : 0.17677669529663687f);  // (C//heads)**-0.5, :187
+    for (int i = tid; i < WPAD * VPT; i += blockDim.x) {
+        const int t = i / VPT, v = i - t * VPT;
+        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+        if (t < WTOK) {
+            const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)stok[t] * (3 * C));
+            q4 = __ldg(src + v);
+            k4 = __ldg(src + VPT + v);
+            v4 = __ldg(src + 2 * VPT + v);
+            __half2* qh = reinterpret_cast<__half2*>(&q4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) qh[e] = __hmul2(qh[e], scale2);  // q * scale in fp16, like the reference
+        }
+        *reinterpret_cast<uint4*>(sq + t * LD + v * 8) = q4;
+        *reinterpret_cast<uint4*>(sk + t * LD + v * 8) = k4;
+        *reinterpret_cast<uint4*>(sv + t * LD + v * 8) = v4;
+    }
+    __syncthreads();
+
+    const int head = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int hc = head * D;
+    // ---- S = Q K^T
+    float s[3][6][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s[mt][nt][r] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < D / 16; ++kt) {
+        uint32_t a[3][4];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+            const __half* p0 = sq + (mt * 16 + g) * LD + hc + kt * 16 + 2 * t4;
+            a[mt][0] = *reinterpret_cast<const uint32_t*>(p0);
+            a[mt][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * LD);
+            a[mt][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+            a[mt][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * LD + 8);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+            const __half* pk = sk + (nt * 8 + g) * LD + hc + kt * 16 + 2 * t4;
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pk);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pk + 8);
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) mma16816(s[mt][nt], a[mt], b0, b1);
+        }
+    }
+    // ---- bias + mask + softmax on the fragments.  element r of (mt, nt): row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1)
+    float inv_sum[3][2];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            const int row = mt * 16 + g + 8 * hlf;
+            const int rq = min(row, WTOK - 1);  // padded query rows compute garbage-free values that are never stored
+            const int qy = rq / WS, qx = rq - qy * WS, qreg = sreg[rq];
+            float mx = -1e30f;
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = nt * 8 + 2 * t4 + e;
+                    float v = s[mt][nt][2 * hlf + e];
+                    if (col < WTOK) {
+                        const int ky = col / WS, kx = col - ky * WS;
+                        v += stab[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head];  // :49-59,:190
+                        if (sreg[col] != qreg) v += -100.0f;                                                   // :204-209
+                    } else {
+                        v = -1e30f;  // padded key
+                    }
+                    s[mt][nt][2 * hlf + e] = v;
+                    mx = fmaxf(mx, v);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float p = __expf(s[mt][nt][2 * hlf + e] - mx);
+                    s[mt][nt][2 * hlf + e] = p;
+                    sum += p;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            inv_sum[mt][hlf] = 1.f / sum;
+        }
+    }
+    // ---- O = P V
+    float o[3][D / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) o[mt][nt][r] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+        uint32_t a[3][4];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+            // normalised probabilities in fp16 (the reference casts the softmax output to fp16 for attn @ v)
+            a[mt][0] = pack_half2(s[mt][2 * kt][0] * inv_sum[mt][0], s[mt][2 * kt][1] * inv_sum[mt][0]);
+            a[mt][1] = pack_half2(s[mt][2 * kt][2] * inv_sum[mt][1], s[mt][2 * kt][3] * inv_sum[mt][1]);
+            a[mt][2] = pack_half2(s[mt][2 * kt + 1][0] * inv_sum[mt][0], s[mt][2 * kt + 1][1] * inv_sum[mt][0]);
+            a[mt][3] = pack_half2(s[mt][2 * kt + 1][2] * inv_sum[mt][1], s[mt][2 * kt + 1][3] * inv_sum[mt][1]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt) {
+            uint32_t b0, b1;
+            ldmatrix_x2_trans(b0, b1, sv + (kt * 16 + (lane & 15)) * LD + hc + nt * 8);
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) mma16816(o[mt][nt], a[mt], b0, b1);
+        }
+    }
+    // ---- stage the head's output columns into sq (each warp owns its own columns), then coalesced stores
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt) {
+            __half* p0 = sq + (mt * 16 + g) * LD + hc + nt * 8 + 2 * t4;
+            *reinterpret_cast<uint32_t*>(p0) = pack_half2(o[mt][nt][0], o[mt][nt][1]);
+            *reinterpret_cast<uint32_t*>(p0 + 8 * LD) = pack_half2(o[mt][nt][2], o[mt][nt][3]);
+        }
+    __syncthreads();
+    for (int i = tid; i < WTOK * VPT; i += blockDim.x) {
+        const int t = i / VPT, v = i - t * VPT;
+        *reinterpret_cast<uint4*>(out + (size_t)stok[t] * C + v * 8) = *reinterpret_cast<const uint4*>(sq + t * LD + v * 8);
+    }
+}
+
+template <int D>
+static size_t attn_smem_bytes() {
+    constexpr int C = D * HEADS, LD = C + 8;
+    return (size_t)3 * WPAD * LD * 2 + 121 * HEADS * 4 + (WTOK + WPAD) * 4 + 16;
+}
+
+int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table, __half* out, int B, int H, int W, int C,
+                     int shift) {
+    NB_CHECK(H % WS == 0 && W % WS == 0, "feature map must be a multiple of the 6x6 window");
+    NB_CHECK(C == 96 || C == 192, "window attention supports C=96 (d=16) and C=192 (d=32)");
+    if (WS >= H) shift = 0;  // torchvision :151-155
+    dim3 grid((H / WS) * (W / WS), B);
+    ProfScope ps(st, PC_ATTN, (double)B * H * W * C * 4 * 2);  // bytes: read q,k,v + write out
+    if (C == 96) {
+        static bool cfg = false;
+        if (!cfg) { NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>())); cfg = true; }
+        window_attention_mma_kernel<16><<<grid, 192, attn_smem_bytes<16>(), st>>>(qkv, bias_table, out, H, W, shift);
+    } else {
+        static bool cfg = false;
+        if (!cfg) { NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<32>())); cfg = true; }
+        window_attention_mma_kernel<32><<<grid, 192, attn_smem_bytes<32>(), st>>>(qkv, bias_table, out, H, W, shift);
+    }
+    NB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace nb200

@@ -86,6 +86,7 @@ int stem_conv3x3(cudaStream_t st, const __half* x, const float* wt, const float*
 // ---------------------------------------------------------------------------------------------
 constexpr int WS = 6, WTOK = 36, HEADS = 6;
 
+#if 0  // round-1 CUDA-core version, superseded by the tensor-core kernel in swin_attention_mma.cu
 template <int D>  // head dim: 16 (C=96) or 32 (C=192)
 __global__ void __launch_bounds__(224) window_attention_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias_table,
                                                                __half* __restrict__ out, int H, int W, int shift) {
@@ -209,6 +210,7 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table
     NB_LAUNCHED();
     return 0;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // ToImage tail: y [n][Hs][Ws][cs] fp16 with channel = c*r*r + dy*r + dx (F.pixel_shuffle) ->

@@ -98,3 +98,48 @@ def test_convT2_pixshuf_with_cropped_skip(B, H, Cin, cout, crop):
     err = (out.float() - ref).abs().max().item()
     log_metric("gemm_convT2", H=H, Cin=Cin, cout=cout, err=err)
     assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("B,H,W,C,shift", [(2, 12, 12, 96, 0), (2, 12, 18, 96, 3), (1, 24, 24, 192, 0), (3, 18, 12, 192, 3),
+                                             (1, 6, 6, 192, 3)])
+def test_window_attention_core(B, H, W, C, shift):
+    """qkv -> attention output (pre-projection) against a torch fp32 evaluation of torchvision's
+    shifted_window_attention body (swin_transformer.py:166-221)."""
+    heads, ws = 6, 6
+    d = C // heads
+    g = torch.Generator(device="cpu").manual_seed(C + H + shift)
+    qkv = torch.randn(B, H, W, 3 * C, generator=g).half().to(DEV)
+    table = (torch.randn(121, heads, generator=g) * 0.5).to(DEV)
+    out = torch.full((B, H, W, C), 9.0, dtype=torch.float16, device=DEV)
+    _lib.check(_lib.lib().nb200_window_attention_f16(_lib.ptr(qkv), _lib.ptr(table), _lib.ptr(out), B, H, W, C, heads, shift,
+                                                     _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    from nunif_b200.synth import relative_position_index
+    s = shift if ws < H else 0
+    x = qkv.float()
+    if s > 0:
+        x = torch.roll(x, shifts=(-s, -s), dims=(1, 2))
+    nh, nw = H // ws, W // ws
+    xw = x.view(B, nh, ws, nw, ws, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(B * nh * nw, ws * ws, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = xw[0] * d ** -0.5, xw[1], xw[2]
+    attn = q @ k.transpose(-2, -1)
+    idx = relative_position_index(ws).to(DEV)
+    attn = attn + table[idx].view(ws * ws, ws * ws, -1).permute(2, 0, 1).unsqueeze(0)
+    if s > 0:
+        m = torch.zeros((H, W), device=DEV)
+        cnt = 0
+        for hs in ((0, -ws), (-ws, -s), (-s, None)):
+            for ws_ in ((0, -ws), (-ws, -s), (-s, None)):
+                m[hs[0]:hs[1], ws_[0]:ws_[1]] = cnt
+                cnt += 1
+        m = m.view(nh, ws, nw, ws).permute(0, 2, 1, 3).reshape(nh * nw, ws * ws)
+        m = m.unsqueeze(1) - m.unsqueeze(2)
+        m = m.masked_fill(m != 0, -100.0).masked_fill(m == 0, 0.0)
+        attn = (attn.view(B, nh * nw, heads, ws * ws, ws * ws) + m.unsqueeze(1).unsqueeze(0)).view(-1, heads, ws * ws, ws * ws)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, ws * ws, C)
+    o = o.view(B, nh, nw, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if s > 0:
+        o = torch.roll(o, shifts=(s, s), dims=(1, 2))
+    err = (out.float() - o).abs().max().item()
+    log_metric("window_attention", H=H, W=W, C=C, shift=shift, err=err)
+    assert err < 1e-2, err
