@@ -142,10 +142,16 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         NB_CHECK(g.cout % 16 == 0 && g.N == 4 * g.cout, "pixel-shuffle: N must be 4*cout, cout % 16 == 0");
     }
     NB_CHECK(g.ldo % 8 == 0 && (!g.res || g.ldr % 8 == 0), "channel strides must be multiples of 8");
-    const int bn = pick_block_n(g.N);
+    // largest BLOCK_N dividing N whose store chunk (64/32/16 columns) does not straddle a pixel-shuffle group
+    int bn = 0, cw = 0;
+    {
+        static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
+        for (int c : cands) {
+            const int w = (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : 16);
+            if (g.N % c == 0 && (!shuf || g.cout % w == 0)) { bn = c; cw = w; break; }
+        }
+    }
     NB_CHECK(bn > 0, "no BLOCK_N divides N");
-    const int cw = (bn % 64 == 0) ? 64 : ((bn % 32 == 0) ? 32 : 16);
-    NB_CHECK(!shuf || g.cout % cw == 0, "pixel-shuffle: cout must be a multiple of the store chunk");
     p.n_tiles = g.N / bn;
     box[0] = BK; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
     GemmMaps maps;

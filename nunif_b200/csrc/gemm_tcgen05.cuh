@@ -13,7 +13,7 @@
 //              128B/64B hardware swizzle, mbarrier complete_tx
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 per instr),
 //              tcgen05.commit releases smem stages and finally signals the epilogue
-//   warps 2-5: epilogue - tcgen05.ld accumulator rows, bias + activation (+ residual tile fetched by TMA),
+//   warps 2-9: epilogue - tcgen05.ld accumulator rows, bias + activation (+ residual tile fetched by TMA),
 //              fp16 results staged in 128B-swizzled shared memory and written with TMA tensor stores
 //              (cp.async.bulk.tensor ... bulk_group), so every global access of the kernel is a full-line bulk copy
 // Non-persistent, one 128 x BLOCK_N output tile per CTA; shared memory is sized so that two CTAs
@@ -101,7 +101,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -158,16 +158,39 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7), with MUFU rcp/ex2: ~16 instructions instead of erff's ~40.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float a = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = 1.0f - poly * t * __expf(-a * a);   // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(e, x));           // nn.GELU (erf form), torchvision MLP swin_transformer.py:444
+}
+
+// activation over a 16-value fragment; `act` is warp-uniform, so the switch is hoisted out of the element loop
+__device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
     switch (act) {
-        case ACT_LRELU01: return v > 0.f ? v : 0.1f * v;
-        case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // nn.GELU (erf form)
-        case ACT_RELU: return fmaxf(v, 0.f);
-        default: return v;
+        case ACT_LRELU01:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
+            break;
+        case ACT_GELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+            break;
+        case ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+        default: break;
     }
 }
 
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                       // two warps per TMEM lane group, each takes every other 16-column block
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 template <int BLOCK_N, int BK>
 struct GemmCfg {
@@ -274,8 +297,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
             __syncwarp();
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int lane_grp = warp & 3;       // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+        const int half = (warp - 2) >> 2;    // which 16-column blocks of the row this warp converts
         const int r = lane_grp * 32 + lane;  // accumulator row == pixel within the tile == staging row
         const bool leader = (warp == 2 && lane == 0);
         mbar_wait(tmem_full_bar, 0);         // all MMAs retired => every pipeline stage is drained and reusable
@@ -295,66 +319,74 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
             mbar_wait(res_bar, 0);
         }
         const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        const int act = p.act;
+        const bool has_res = p.has_res != 0, res_first = p.res_before_act != 0;
 #pragma unroll 1
-        for (int c = 0; c < Cfg::NCH; ++c) {
+        for (int sb = half; sb < BLOCK_N / 16; sb += 2) {
+            uint32_t acc[16];
+            tmem_ld16(trow + sb * 16, acc);
+            tmem_ld_wait();
+            const int c = (sb * 16) / CW, sub = sb - c * (CW / 16);
             uint8_t* buf = stg + c * Cfg::CH_BYTES;
+            uint4* s0 = reinterpret_cast<uint4*>(buf + stage_off<CW>(r, 2 * sub));
+            uint4* s1 = reinterpret_cast<uint4*>(buf + stage_off<CW>(r, 2 * sub + 1));
+            float v[16];
+            if (p.bias) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + sb * 16);
 #pragma unroll
-            for (int sub = 0; sub < CW / 16; ++sub) {
-                uint32_t acc[16];
-                tmem_ld16(trow + c * CW + sub * 16, acc);
-                tmem_ld_wait();
-                const int n = n0 + c * CW + sub * 16;
-                float v[16];
-                if (p.bias) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n) + q);
-                        v[4 * q] = __uint_as_float(acc[4 * q]) + bq.x;
-                        v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + bq.y;
-                        v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + bq.z;
-                        v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + bq.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bq = __ldg(bp + q);
+                    v[4 * q] = __uint_as_float(acc[4 * q]) + bq.x;
+                    v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + bq.y;
+                    v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + bq.z;
+                    v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + bq.w;
                 }
-                uint4* s0 = reinterpret_cast<uint4*>(buf + stage_off<CW>(r, 2 * sub));
-                uint4* s1 = reinterpret_cast<uint4*>(buf + stage_off<CW>(r, 2 * sub + 1));
-                float rv[16];
-                if (p.has_res) {
-                    const uint4 r0 = *s0, r1 = *s1;
-                    const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-                    const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 a = __half22float2(h0[j]), d = __half22float2(h1[j]);
-                        rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = d.x; rv[8 + 2 * j + 1] = d.y;
-                    }
-                }
-                __align__(16) __half2 o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float a0 = v[2 * j], a1 = v[2 * j + 1];
-                    if (p.has_res && p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
-                    a0 = apply_act(a0, p.act);
-                    a1 = apply_act(a1, p.act);
-                    if (p.has_res && !p.res_before_act) { a0 += rv[2 * j]; a1 += rv[2 * j + 1]; }
-                    o[j] = __floats2half2_rn(a0, a1);
-                }
-                *s0 = reinterpret_cast<const uint4*>(o)[0];
-                *s1 = reinterpret_cast<const uint4*>(o)[1];
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
             }
-            fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-            epi_bar_sync();
-            if (leader) {
+            if (has_res) {
+                float rv[16];
+                const uint4 r0 = *s0, r1 = *s1;
+                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a = __half22float2(h0[j]), d = __half22float2(h1[j]);
+                    rv[2 * j] = a.x; rv[2 * j + 1] = a.y; rv[8 + 2 * j] = d.x; rv[8 + 2 * j + 1] = d.y;
+                }
+                if (res_first) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                    apply_act16(v, act);
+                } else {
+                    apply_act16(v, act);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += rv[j];
+                }
+            } else {
+                apply_act16(v, act);
+            }
+            __align__(16) __half2 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            *s0 = reinterpret_cast<const uint4*>(o)[0];
+            *s1 = reinterpret_cast<const uint4*>(o)[1];
+        }
+        fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (leader) {
+#pragma unroll 1
+            for (int c = 0; c < Cfg::NCH; ++c) {
                 const int n = n0 + c * CW;
                 const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
                 const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
-                tma_store_4d(&maps.o[g], buf, co, x0, y0, b);  // out-of-range rows/cols of edge tiles are clipped by TMA
-                tma_store_commit();
+                // out-of-range rows/cols of edge tiles are clipped by TMA
+                tma_store_4d(&maps.o[g], stg + c * Cfg::CH_BYTES, co, x0, y0, b);
             }
+            tma_store_commit();
+            tma_store_wait_read();  // smem must stay valid until the bulk stores have read it
         }
-        if (leader) tma_store_wait_read();  // smem must stay valid until the bulk stores have read it
         tc_fence_before();
     }
     __syncthreads();

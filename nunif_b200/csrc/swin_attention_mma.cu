@@ -1,6 +1,8 @@
 // Shifted-window attention core on tensor cores (mma.sync m16n8k16, fp16 in / fp32 accumulate).
 //
-// One CTA per 6x6 window, one warp per head (6 warps).  The 36 tokens are padded to 48 rows:
+// One CTA per 6x6 window, one warp per head (6 warps), 3 CTAs per SM.  q/k/v rows are staged with
+// cp.async (16-byte LDGSTS, no register round trip).  The 36 tokens are padded to 48 MMA rows by clamping
+// the row index (padded keys are masked by select, padded probabilities are exactly 0):
 //   S = (Q*scale) K^T : M=48 (3 m16 tiles), N=48 (6 n8 tiles), K=d (d/16 steps)
 //   softmax on the accumulator fragments (quad shuffles), relative-position bias and the
 //   shift mask added per element, padded keys masked out
@@ -36,16 +38,21 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 }  // namespace
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 template <int D>
-__global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias_table,
+__global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias_table,
                                                                    __half* __restrict__ out, int H, int W, int shift) {
     constexpr int C = D * HEADS;
     constexpr int LD = C + 8;  // padded row: (C+8)*2 bytes = 4 words mod 32 banks -> conflict-free fragment loads
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __half* sq = reinterpret_cast<__half*>(smem_raw);  // [WPAD][LD]  (q*scale), later the output tile
-    __half* sk = sq + WPAD * LD;
-    __half* sv = sk + WPAD * LD;
-    float* stab = reinterpret_cast<float*>(sv + WPAD * LD);  // [121][HEADS]
+    __half* sq = reinterpret_cast<__half*>(smem_raw);  // [WTOK][LD]  q, later the output tile
+    __half* sk = sq + WTOK * LD;
+    __half* sv = sk + WTOK * LD;
+    float* stab = reinterpret_cast<float*>(sv + WTOK * LD);  // [121][HEADS]
     int* stok = reinterpret_cast<int*>(stab + 121 * HEADS);  // [WTOK]
     int* sreg = stok + WTOK;                                 // [WPAD]
     const int nww = W / WS;
@@ -68,25 +75,16 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
     }
     for (int i = tid; i < 121 * HEADS; i += blockDim.x) stab[i] = bias_table[i];
     __syncthreads();
-    // ---- stage q*scale, k, v (16-byte vectors; one token row = 3C contiguous halves in global)
+    // ---- stage q, k, v: one token row = 3C contiguous halves in global, 16-byte cp.async each
     constexpr int VPT = C / 8;
-    const __half2 scale2 = __float2half2_rn(D == 16 ? 0.25f : 0.17677669529663687f);  // (C//heads)**-0.5, :187
-    for (int i = tid; i < WPAD * VPT; i += blockDim.x) {
-        const int t = i / VPT, v = i - t * VPT;
-        uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
-        if (t < WTOK) {
-            const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)stok[t] * (3 * C));
-            q4 = __ldg(src + v);
-            k4 = __ldg(src + VPT + v);
-            v4 = __ldg(src + 2 * VPT + v);
-            __half2* qh = reinterpret_cast<__half2*>(&q4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) qh[e] = __hmul2(qh[e], scale2);  // q * scale in fp16, like the reference
-        }
-        *reinterpret_cast<uint4*>(sq + t * LD + v * 8) = q4;
-        *reinterpret_cast<uint4*>(sk + t * LD + v * 8) = k4;
-        *reinterpret_cast<uint4*>(sv + t * LD + v * 8) = v4;
+    for (int i = tid; i < WTOK * 3 * VPT; i += blockDim.x) {
+        const int t = i / (3 * VPT), v = i - t * (3 * VPT);
+        const int m = v / VPT, vv = v - m * VPT;  // m: 0 = q, 1 = k, 2 = v
+        __half* dst = (m == 0 ? sq : (m == 1 ? sk : sv)) + t * LD + vv * 8;
+        cp_async16(dst, qkv + (size_t)stok[t] * (3 * C) + v * 8);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int head = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
@@ -104,15 +102,16 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
         uint32_t a[3][4];
 #pragma unroll
         for (int mt = 0; mt < 3; ++mt) {
-            const __half* p0 = sq + (mt * 16 + g) * LD + hc + kt * 16 + 2 * t4;
+            const __half* p0 = sq + min(mt * 16 + g, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
+            const __half* p1 = sq + min(mt * 16 + g + 8, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
             a[mt][0] = *reinterpret_cast<const uint32_t*>(p0);
-            a[mt][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * LD);
+            a[mt][1] = *reinterpret_cast<const uint32_t*>(p1);
             a[mt][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
-            a[mt][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * LD + 8);
+            a[mt][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
         }
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt) {
-            const __half* pk = sk + (nt * 8 + g) * LD + hc + kt * 16 + 2 * t4;
+            const __half* pk = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
             const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pk);
             const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pk + 8);
 #pragma unroll
@@ -120,6 +119,7 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
         }
     }
     // ---- bias + mask + softmax on the fragments.  element r of (mt, nt): row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1)
+    const float scale = (D == 16) ? 0.25f : 0.17677669529663687f;  // (C // heads) ** -0.5 (:187), applied to S in fp32
     float inv_sum[3][2];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
                     float v = s[mt][nt][2 * hlf + e];
                     if (col < WTOK) {
                         const int ky = col / WS, kx = col - ky * WS;
-                        v += stab[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head];  // :49-59,:190
+                        v = fmaf(v, scale, stab[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head]);  // :187,:49-59,:190
                         if (sreg[col] != qreg) v += -100.0f;                                                   // :204-209
                     } else {
                         v = -1e30f;  // padded key
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
 #pragma unroll
         for (int nt = 0; nt < D / 8; ++nt) {
             uint32_t b0, b1;
-            ldmatrix_x2_trans(b0, b1, sv + (kt * 16 + (lane & 15)) * LD + hc + nt * 8);
+            ldmatrix_x2_trans(b0, b1, sv + min(kt * 16 + (lane & 15), WTOK - 1) * LD + hc + nt * 8);
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt) mma16816(o[mt][nt], a[mt], b0, b1);
         }
@@ -194,9 +194,9 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
     for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
         for (int nt = 0; nt < D / 8; ++nt) {
-            __half* p0 = sq + (mt * 16 + g) * LD + hc + nt * 8 + 2 * t4;
-            *reinterpret_cast<uint32_t*>(p0) = pack_half2(o[mt][nt][0], o[mt][nt][1]);
-            *reinterpret_cast<uint32_t*>(p0 + 8 * LD) = pack_half2(o[mt][nt][2], o[mt][nt][3]);
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            if (r0 < WTOK) *reinterpret_cast<uint32_t*>(sq + r0 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[mt][nt][0], o[mt][nt][1]);
+            if (r1 < WTOK) *reinterpret_cast<uint32_t*>(sq + r1 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[mt][nt][2], o[mt][nt][3]);
         }
     __syncthreads();
     for (int i = tid; i < WTOK * VPT; i += blockDim.x) {
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(192) window_attention_mma_kernel(const __half*
 template <int D>
 static size_t attn_smem_bytes() {
     constexpr int C = D * HEADS, LD = C + 8;
-    return (size_t)3 * WPAD * LD * 2 + 121 * HEADS * 4 + (WTOK + WPAD) * 4 + 16;
+    return (size_t)3 * WTOK * LD * 2 + 121 * HEADS * 4 + (WTOK + WPAD) * 4 + 16;
 }
 
 int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table, __half* out, int B, int H, int W, int C,
@@ -220,11 +220,19 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table
     ProfScope ps(st, PC_ATTN, (double)B * H * W * C * 4 * 2);  // bytes: read q,k,v + write out
     if (C == 96) {
         static bool cfg = false;
-        if (!cfg) { NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>())); cfg = true; }
+        if (!cfg) {
+            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>()));
+            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            cfg = true;
+        }
         window_attention_mma_kernel<16><<<grid, 192, attn_smem_bytes<16>(), st>>>(qkv, bias_table, out, H, W, shift);
     } else {
         static bool cfg = false;
-        if (!cfg) { NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<32>())); cfg = true; }
+        if (!cfg) {
+            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<32>()));
+            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            cfg = true;
+        }
         window_attention_mma_kernel<32><<<grid, 192, attn_smem_bytes<32>(), st>>>(qkv, bias_table, out, H, W, shift);
     }
     NB_LAUNCHED();
