@@ -1,7 +1,9 @@
 // Host side of the tcgen05 implicit-GEMM: tensor-map construction and dispatch.
 #include "gemm.h"
 #include "gemm_tcgen05.cuh"
+#include "gemm_persistent.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace nb200 {
 
@@ -62,6 +64,78 @@ static int launch_bn(int bn, cudaStream_t st, const GemmMaps& maps, const GemmPa
         case 128: return launch_t<128, BK>(st, maps, p, m_tiles, n_tiles);
         case 192: return launch_t<192, BK>(st, maps, p, m_tiles, n_tiles);
         case 256: return launch_t<256, BK>(st, maps, p, m_tiles, n_tiles);
+    }
+    return fail("unsupported BLOCK_N");
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
+
+template <int BN, int BK, bool RES>
+static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {
+    static int configured = 0;  // per instantiation: largest size configured so far
+    if ((int)smem > configured) {
+        NB_CUDA(cudaFuncSetAttribute(gemm_conv_persistent<BN, BK, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = (int)smem;
+    }
+    pp.stages = stages;
+    gemm_conv_persistent<BN, BK, RES><<<grid, PG_THREADS, smem, st>>>(maps, pp);
+    NB_LAUNCHED();
+    return 0;
+}
+
+template <int BN, int BK>
+static int launch_persistent_t(cudaStream_t st, const GemmMaps& maps, const GemmParams& p, int m_tiles) {
+    using Cfg = GemmCfg<BN, BK>;
+    PersistParams pp;
+    pp.g = p;
+    pp.m_tiles = m_tiles;
+    pp.k_iters = p.taps * p.cpt;
+    int grid_m = num_sms() / p.n_tiles;
+    if (grid_m < 1) grid_m = 1;
+    if (grid_m > m_tiles) grid_m = m_tiles;
+    pp.grid_m = grid_m;
+    const int grid = grid_m * p.n_tiles;
+    constexpr int b_chunk = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
+    const int stg = PG_NSTG * Cfg::CH_BYTES;
+    // weights resident in shared memory when they fit next to >= 3 activation stages
+    const long long bres = (long long)pp.k_iters * b_chunk;
+    const long long room_res = (long long)PG_SMEM_BUDGET - stg - bres;
+    if (room_res >= 3LL * Cfg::A_BYTES) {
+        int stages = (int)(room_res / Cfg::A_BYTES);
+        if (stages > PG_MAX_STAGES) stages = PG_MAX_STAGES;
+        const size_t smem = (size_t)bres + (size_t)stages * Cfg::A_BYTES + stg + 1024 + 512;
+        return launch_p<BN, BK, true>(st, maps, pp, stages, smem, grid);
+    }
+    const int stage_bytes = Cfg::A_BYTES + b_chunk;
+    int stages = (PG_SMEM_BUDGET - stg) / stage_bytes;
+    if (stages > PG_MAX_STAGES) stages = PG_MAX_STAGES;
+    if (stages < 2) return fail("persistent GEMM: tile does not fit shared memory");
+    const size_t smem = (size_t)stages * stage_bytes + stg + 1024 + 512;
+    return launch_p<BN, BK, false>(st, maps, pp, stages, smem, grid);
+}
+
+template <int BK>
+static int launch_persistent_bn(int bn, cudaStream_t st, const GemmMaps& maps, const GemmParams& p, int m_tiles) {
+    switch (bn) {
+        case 16: return launch_persistent_t<16, BK>(st, maps, p, m_tiles);
+        case 32: return launch_persistent_t<32, BK>(st, maps, p, m_tiles);
+        case 48: return launch_persistent_t<48, BK>(st, maps, p, m_tiles);
+        case 64: return launch_persistent_t<64, BK>(st, maps, p, m_tiles);
+        case 96: return launch_persistent_t<96, BK>(st, maps, p, m_tiles);
+        case 128: return launch_persistent_t<128, BK>(st, maps, p, m_tiles);
+        case 192: return launch_persistent_t<192, BK>(st, maps, p, m_tiles);
+        case 256: return launch_persistent_t<256, BK>(st, maps, p, m_tiles);
     }
     return fail("unsupported BLOCK_N");
 }
@@ -191,7 +265,9 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     }
     const int m_tiles = p.tiles_x * p.tiles_y * p.B;
     ProfScope ps(st, PC_GEMM, 2.0 * (double)p.B * p.Ho * p.Wo * (double)g.N * (double)K);
-    return BK == 64 ? launch_bn<64>(bn, st, maps, p, m_tiles, p.n_tiles) : launch_bn<32>(bn, st, maps, p, m_tiles, p.n_tiles);
+    static const bool legacy = getenv("NB200_GEMM_NONPERSISTENT") != nullptr;  // A/B switch for profiling only
+    if (legacy) return BK == 64 ? launch_bn<64>(bn, st, maps, p, m_tiles, p.n_tiles) : launch_bn<32>(bn, st, maps, p, m_tiles, p.n_tiles);
+    return BK == 64 ? launch_persistent_bn<64>(bn, st, maps, p, m_tiles) : launch_persistent_bn<32>(bn, st, maps, p, m_tiles);
 }
 
 }  // namespace nb200

@@ -31,6 +31,7 @@ def act_ref(x, act):
     (1000, 96, 288, 0, False), (129, 192, 576, 0, False), (4096, 192, 192, 0, True), (777, 96, 192, 2, False),
     (2048, 384, 192, 0, True), (640, 192, 768, 0, False), (512, 192, 48, 0, False), (300, 96, 96, 0, True),
     (256, 64, 64, 1, False), (200, 32, 16, 3, False), (57600, 192, 384, 2, False),
+    (200000, 192, 192, 0, True), (150001, 96, 288, 0, False), (99999, 384, 192, 0, True), (64, 192, 576, 0, False),
 ])
 def test_linear_flat(M, K, N, act, use_res):
     g = torch.Generator(device="cpu").manual_seed(M + K + N)
@@ -49,7 +50,7 @@ def test_linear_flat(M, K, N, act, use_res):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,N,act", [(2, 37, 41, 64, 128, 1), (1, 20, 52, 32, 64, 1), (3, 18, 18, 128, 256, 1),
-                                               (1, 30, 30, 256, 128, 0), (2, 26, 26, 64, 96, 1)])
+                                               (1, 30, 30, 256, 128, 0), (2, 26, 26, 64, 96, 1), (4, 130, 134, 64, 64, 1), (16, 50, 50, 128, 64, 1)])
 def test_conv3(B, H, W, Cin, N, act):
     g = torch.Generator(device="cpu").manual_seed(H * W + Cin)
     A = torch.randn(B, H, W, Cin, generator=g).half().to(DEV)
