@@ -10,7 +10,8 @@
 //   * an A ring (TMA producer warp -> MMA warp) that runs ahead across tile boundaries;
 //   * two TMEM accumulators (2 x BLOCK_N columns): the MMA of tile j+1 overlaps the epilogue of tile j;
 //   * 8 epilogue warps; results go through a ring of 128B-swizzled staging chunks and leave with TMA
-//     tensor stores; residual tiles are TMA-prefetched into the same ring by the producer.
+//     tensor stores (the leader only ever waits for the store issued PG_NOUT chunks earlier); residual tiles
+//     are TMA-prefetched by the producer into their own ring, PG_NRES chunks ahead of the epilogue.
 // Every global access is a bulk tensor copy; the kernel is designed to sit on the HBM roofline for the
 // memory-bound Linears (M x {96,192} activations) and on the tensor roofline for the large-K convs.
 #pragma once
@@ -19,7 +20,8 @@
 namespace nb200 {
 
 constexpr int PG_MAX_STAGES = 8;   // A(/B) ring depth upper bound
-constexpr int PG_NSTG = 4;         // staging ring (chunks of [128][CW] fp16)
+constexpr int PG_NOUT = 3;         // output staging ring (chunks of [128][CW] fp16 waiting for their TMA store)
+constexpr int PG_NRES = 3;         // residual prefetch ring (same chunk shape), only allocated when a residual exists
 constexpr int PG_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 struct PersistParams {
@@ -45,15 +47,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;                                               // resident weights: k_iters chunks of B_BYTES
     uint8_t* sRing = sB + (RESIDENT_B ? k_iters * B_BYTES : 0);       // SA stages
-    uint8_t* sStg = sRing + SA * STAGE_BYTES;                         // PG_NSTG staging chunks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + PG_NSTG * CH_BYTES);
+    uint8_t* sOut = sRing + SA * STAGE_BYTES;                         // PG_NOUT output staging chunks
+    uint8_t* sRes = sOut + PG_NOUT * CH_BYTES;                        // PG_NRES residual chunks (if has_res)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (p.has_res ? PG_NRES * CH_BYTES : 0));
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + PG_MAX_STAGES;
     uint64_t* acc_full = a_empty + PG_MAX_STAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint64_t* stg_full = acc_empty + 2;
-    uint64_t* stg_empty = stg_full + PG_NSTG;
-    uint64_t* b_full = stg_empty + PG_NSTG;
+    uint64_t* res_full = acc_empty + 2;
+    uint64_t* res_empty = res_full + PG_NRES;
+    uint64_t* out_empty = res_empty + PG_NRES;
+    uint64_t* b_full = out_empty + PG_NOUT;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,10 +79,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 1);
         }
-        for (int s = 0; s < PG_NSTG; ++s) {
-            mbar_init(&stg_full[s], 1);
-            mbar_init(&stg_empty[s], 1);
+        for (int s = 0; s < PG_NRES; ++s) {
+            mbar_init(&res_full[s], 1);
+            mbar_init(&res_empty[s], 1);
         }
+        for (int s = 0; s < PG_NOUT; ++s) mbar_init(&out_empty[s], 1);
         mbar_init(b_full, 1);
         fence_barrier_init();
     }
@@ -110,15 +115,15 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                     if (!RESIDENT_B) tma_load_2d(&maps.b, &a_full[s], sa + A_BYTES, it * BK, n0);
                 }
                 if (p.has_res) {
-                    // residual chunks of this tile go straight into the staging ring (the epilogue adds in place)
+                    // residual chunks of this tile, prefetched PG_NRES chunks ahead of the epilogue
                     for (int c = 0; c < NCH; ++c, ++cq) {
-                        const int buf = cq % PG_NSTG;
-                        mbar_wait(&stg_empty[buf], ((cq / PG_NSTG) & 1) ^ 1);
+                        const int buf = cq % PG_NRES;
+                        mbar_wait(&res_empty[buf], ((cq / PG_NRES) & 1) ^ 1);
                         const int n = n0 + c * CW;
                         const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
                         const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
-                        mbar_expect_tx(&stg_full[buf], CH_BYTES);
-                        tma_load_4d(&maps.r[g], &stg_full[buf], sStg + buf * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
+                        mbar_expect_tx(&res_full[buf], CH_BYTES);
+                        tma_load_4d(&maps.r[g], &res_full[buf], sRes + buf * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
                     }
                 }
             }
@@ -174,18 +179,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c, ++cq) {
-                const int buf = cq % PG_NSTG;
-                const uint32_t ph = (cq / PG_NSTG) & 1;
-                if (has_res) mbar_wait(&stg_full[buf], ph);        // residual chunk landed
-                else mbar_wait(&stg_empty[buf], ph ^ 1);          // previous store out of this buffer has been read
-                uint8_t* bufp = sStg + buf * CH_BYTES;
+                const int buf = cq % PG_NOUT, rbuf = cq % PG_NRES;
+                mbar_wait(&out_empty[buf], ((cq / PG_NOUT) & 1) ^ 1);     // the store issued PG_NOUT chunks ago has read this buffer
+                if (has_res) mbar_wait(&res_full[rbuf], (cq / PG_NRES) & 1);  // residual chunk landed
+                uint8_t* bufp = sOut + buf * CH_BYTES;
+                const uint8_t* resp = sRes + rbuf * CH_BYTES;
 #pragma unroll 1
                 for (int sub = half; sub < CW / 16; sub += 2) {
                     uint32_t acc[16];
                     tmem_ld16(trow + c * CW + sub * 16, acc);
                     tmem_ld_wait();
-                    uint4* s0 = reinterpret_cast<uint4*>(bufp + stage_off<CW>(r, 2 * sub));
-                    uint4* s1 = reinterpret_cast<uint4*>(bufp + stage_off<CW>(r, 2 * sub + 1));
+                    const uint32_t o0 = stage_off<CW>(r, 2 * sub), o1 = stage_off<CW>(r, 2 * sub + 1);
+                    uint4* s0 = reinterpret_cast<uint4*>(bufp + o0);
+                    uint4* s1 = reinterpret_cast<uint4*>(bufp + o1);
                     float v[16];
                     if (p.bias) {
                         const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * CW + sub * 16);
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                     }
                     if (has_res) {
                         float rv[16];
-                        const uint4 r0 = *s0, r1 = *s1;
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(resp + o0), r1 = *reinterpret_cast<const uint4*>(resp + o1);
                         const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
                         const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
@@ -234,16 +240,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                 epi_bar_sync();
                 if (leader) {
                     if (c == NCH - 1) mbar_arrive(&acc_empty[a]);  // hand the accumulator back to the MMA warp
+                    if (has_res) mbar_arrive(&res_empty[rbuf]);    // residual chunk consumed by every epilogue thread
                     const int n = n0 + c * CW;
                     const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
                     const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
                     tma_store_4d(&maps.o[g], bufp, co, x0, y0, b);
                     tma_store_commit();
-                    // every store but the newest has finished reading its staging buffer: hand those buffers back
-                    // (to the producer for residual prefetch, or to the epilogue itself)
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    while (released + 1 <= cq) {
-                        mbar_arrive(&stg_empty[released % PG_NSTG]);
+                    // all but the PG_NOUT-1 newest stores have read their staging buffers: hand those buffers back.
+                    // The next chunk needs exactly the oldest of them, so this wait is (almost) never blocking.
+                    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PG_NOUT - 1) : "memory");
+                    while (released + (PG_NOUT - 1) <= cq) {
+                        mbar_arrive(&out_empty[released % PG_NOUT]);
                         ++released;
                     }
                 }

@@ -218,7 +218,28 @@ static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std
         b.fc1 = pack_linear(pk, p + ".mlp.0", 2 * C, C);
         b.fc2 = pack_linear(pk, p + ".mlp.3", C, 2 * C);
         const float* t = pk.get(p + ".attn.relative_position_bias_table", 121 * 6);
-        if (t) b.table = pk.add_f32(std::vector<float>(t, t + 121 * 6));
+        if (t) {
+            // relative-position bias expanded once into the attention kernel's accumulator-fragment order
+            // (same layout as build_bias_frag_kernel in swin_attention_mma.cu): [head][mt][nt][lane][4]
+            std::vector<float> frag(BIAS_FRAG_FLOATS);
+            for (int head = 0; head < 6; ++head)
+                for (int mt = 0; mt < 3; ++mt)
+                    for (int nt = 0; nt < 6; ++nt)
+                        for (int lane = 0; lane < 32; ++lane)
+                            for (int r = 0; r < 4; ++r) {
+                                const int g = lane >> 2, t4 = lane & 3;
+                                const int row = mt * 16 + g + 8 * (r >> 1), col = nt * 8 + 2 * t4 + (r & 1);
+                                float v;
+                                if (col >= 36) v = -1e30f;
+                                else if (row >= 36) v = 0.f;
+                                else {
+                                    const int qy = row / 6, qx = row % 6, ky = col / 6, kx = col % 6;
+                                    v = 1.4426950408889634f * t[((qy - ky + 5) * 11 + (qx - kx + 5)) * 6 + head];
+                                }
+                                frag[((((size_t)head * 3 + mt) * 6 + nt) * 32 + lane) * 4 + r] = v;
+                            }
+            b.table = pk.add_f32(frag);
+        }
         pk.mark(p + ".attn.relative_position_index");  // buffer; the kernel recomputes the index (swin_transformer.py:267-279)
         out.push_back(b);
     }

@@ -44,7 +44,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 template <int D>
-__global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias_table,
+__global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
                                                                    __half* __restrict__ out, int H, int W, int shift) {
     constexpr int C = D * HEADS;
     constexpr int LD = C + 8;  // padded row: (C+8)*2 bytes = 4 words mod 32 banks -> conflict-free fragment loads
@@ -52,8 +52,7 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
     __half* sq = reinterpret_cast<__half*>(smem_raw);  // [WTOK][LD]  q, later the output tile
     __half* sk = sq + WTOK * LD;
     __half* sv = sk + WTOK * LD;
-    float* stab = reinterpret_cast<float*>(sv + WTOK * LD);  // [121][HEADS]
-    int* stok = reinterpret_cast<int*>(stab + 121 * HEADS);  // [WTOK]
+    int* stok = reinterpret_cast<int*>(sv + WTOK * LD);      // [WTOK]
     int* sreg = stok + WTOK;                                 // [WPAD]
     const int nww = W / WS;
     const int wx = blockIdx.x % nww, wy = blockIdx.x / nww, b = blockIdx.y;
@@ -73,7 +72,6 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
         }
         sreg[tid] = reg;
     }
-    for (int i = tid; i < 121 * HEADS; i += blockDim.x) stab[i] = bias_table[i];
     __syncthreads();
     // ---- stage q, k, v: one token row = 3C contiguous halves in global, 16-byte cp.async each
     constexpr int VPT = C / 8;
@@ -119,32 +117,49 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
         }
     }
     // ---- bias + mask + softmax on the fragments.  element r of (mt, nt): row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1)
-    const float scale = (D == 16) ? 0.25f : 0.17677669529663687f;  // (C // heads) ** -0.5 (:187), applied to S in fp32
+    // bias_frag holds log2(e) * relative_position_bias in exactly this fragment order (padded keys = -1e30), so the
+    // whole "scale, add bias, mask padding" step is one FMA per element and the softmax runs in base 2.
+    const float scale = ((D == 16) ? 0.25f : 0.17677669529663687f) * 1.4426950408889634f;  // (C//heads)**-0.5 (:187) * log2(e)
+    {
+        const float4* bf = bias_frag + (size_t)head * (3 * 6 * 32) + lane;
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt) {
+                const float4 bv = __ldg(bf + (mt * 6 + nt) * 32);
+                s[mt][nt][0] = fmaf(s[mt][nt][0], scale, bv.x);
+                s[mt][nt][1] = fmaf(s[mt][nt][1], scale, bv.y);
+                s[mt][nt][2] = fmaf(s[mt][nt][2], scale, bv.z);
+                s[mt][nt][3] = fmaf(s[mt][nt][3], scale, bv.w);
+            }
+    }
+    if (shift > 0 && (wy == gridDim.x / nww - 1 || wx == nww - 1)) {
+        // only the last window row / column of a shifted map mixes regions (:193-209): -100 across regions
+        int creg[6][2];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) creg[nt][e] = sreg[min(nt * 8 + 2 * t4 + e, WTOK - 1)];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const int qreg = sreg[min(mt * 16 + g + 8 * hlf, WTOK - 1)];
+#pragma unroll
+                for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (creg[nt][e] != qreg) s[mt][nt][2 * hlf + e] += -100.0f * 1.4426950408889634f;
+            }
+    }
     float inv_sum[3][2];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt) {
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
-            const int row = mt * 16 + g + 8 * hlf;
-            const int rq = min(row, WTOK - 1);  // padded query rows compute garbage-free values that are never stored
-            const int qy = rq / WS, qx = rq - qy * WS, qreg = sreg[rq];
             float mx = -1e30f;
 #pragma unroll
-            for (int nt = 0; nt < 6; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = nt * 8 + 2 * t4 + e;
-                    float v = s[mt][nt][2 * hlf + e];
-                    if (col < WTOK) {
-                        const int ky = col / WS, kx = col - ky * WS;
-                        v = fmaf(v, scale, stab[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head]);  // :187,:49-59,:190
-                        if (sreg[col] != qreg) v += -100.0f;                                                   // :204-209
-                    } else {
-                        v = -1e30f;  // padded key
-                    }
-                    s[mt][nt][2 * hlf + e] = v;
-                    mx = fmaxf(mx, v);
-                }
+            for (int nt = 0; nt < 6; ++nt) mx = fmaxf(mx, fmaxf(s[mt][nt][2 * hlf], s[mt][nt][2 * hlf + 1]));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             float sum = 0.f;
@@ -152,9 +167,9 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
             for (int nt = 0; nt < 6; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float p = __expf(s[mt][nt][2 * hlf + e] - mx);
-                    s[mt][nt][2 * hlf + e] = p;
-                    sum += p;
+                    const float pe = exp2f(s[mt][nt][2 * hlf + e] - mx);
+                    s[mt][nt][2 * hlf + e] = pe;
+                    sum += pe;
                 }
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -205,14 +220,43 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
     }
 }
 
+// bias_frag[head][mt][nt][lane] (float4 = accumulator fragment order) = log2(e) * table[rel_index(row, col)][head];
+// padded key columns (>= 36) hold -1e30 so they vanish in the softmax; padded query rows hold 0.
+__global__ void build_bias_frag_kernel(const float* __restrict__ table, float4* __restrict__ frag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // ((head*3 + mt)*6 + nt)*32 + lane
+    if (i >= HEADS * 3 * 6 * 32) return;
+    const int lane = i & 31, nt = (i >> 5) % 6, mt = (i / (32 * 6)) % 3, head = i / (32 * 6 * 3);
+    const int g = lane >> 2, t4 = lane & 3;
+    float v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = mt * 16 + g + 8 * (r >> 1), col = nt * 8 + 2 * t4 + (r & 1);
+        if (col >= WTOK) v[r] = -1e30f;
+        else if (row >= WTOK) v[r] = 0.f;
+        else {
+            const int qy = row / WS, qx = row % WS, ky = col / WS, kx = col % WS;
+            // relative_position_index (swin_transformer.py:267-279)
+            v[r] = 1.4426950408889634f * table[((qy - ky + WS - 1) * (2 * WS - 1) + (qx - kx + WS - 1)) * HEADS + head];
+        }
+    }
+    frag[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+int build_bias_frag(cudaStream_t st, const float* table, float* frag) {
+    build_bias_frag_kernel<<<(HEADS * 3 * 6 * 32 + 255) / 256, 256, 0, st>>>(table, reinterpret_cast<float4*>(frag));
+    NB_LAUNCHED();
+    return 0;
+}
+
 template <int D>
 static size_t attn_smem_bytes() {
     constexpr int C = D * HEADS, LD = C + 8;
-    return (size_t)3 * WTOK * LD * 2 + 121 * HEADS * 4 + (WTOK + WPAD) * 4 + 16;
+    return (size_t)3 * WTOK * LD * 2 + (WTOK + WPAD) * 4 + 16;
 }
 
-int window_attention(cudaStream_t st, const __half* qkv, const float* bias_table, __half* out, int B, int H, int W, int C,
+int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_f, __half* out, int B, int H, int W, int C,
                      int shift) {
+    const float4* bias_table = reinterpret_cast<const float4*>(bias_frag_f);
     NB_CHECK(H % WS == 0 && W % WS == 0, "feature map must be a multiple of the 6x6 window");
     NB_CHECK(C == 96 || C == 192, "window attention supports C=96 (d=16) and C=192 (d=32)");
     if (WS >= H) shift = 0;  // torchvision :151-155

@@ -277,6 +277,12 @@ using namespace nb200;
 extern "C" int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B, int H, int W, int C,
                                           int heads, int shift, void* stream) {
     NB_CHECK(qkv && bias_table && out, "null pointer");
-    NB_CHECK(heads == HEADS, "only 6 heads are supported");
-    return window_attention((cudaStream_t)stream, (const __half*)qkv, bias_table, (__half*)out, B, H, W, C, shift);
+    NB_CHECK(heads == 6, "only 6 heads are supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* frag = nullptr;
+    NB_CUDA(cudaMallocAsync((void**)&frag, BIAS_FRAG_FLOATS * sizeof(float), st));
+    int rc = build_bias_frag(st, bias_table, frag);
+    if (!rc) rc = window_attention(st, (const __half*)qkv, frag, (__half*)out, B, H, W, C, shift);
+    cudaFreeAsync(frag, st);
+    return rc;
 }
