@@ -85,6 +85,47 @@ __global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
     }
 }
 
+// 4 horizontally adjacent output pixels per thread (valid when y_w, the tile step and S are multiples of 4, so a
+// group never straddles a tile edge): 8-byte fp16 loads, one float4 store per colour plane.
+__global__ void __launch_bounds__(256) tile_gather_blend4_kernel(BlendParams p) {
+    const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int Y = blockIdx.y;
+    if (X >= p.y_w) return;
+    const int hi1 = min(Y / p.step_out, p.h_blocks - 1);
+    const int wi1 = min(X / p.step_out, p.w_blocks - 1);
+    int his[2], wis[2], nh = 0, nw = 0;
+    if (hi1 > 0 && Y - (hi1 - 1) * p.step_out < p.S) his[nh++] = hi1 - 1;
+    if (Y - hi1 * p.step_out < p.S) his[nh++] = hi1;
+    if (wi1 > 0 && X - (wi1 - 1) * p.step_out < p.S) wis[nw++] = wi1 - 1;
+    if (X - wi1 * p.step_out < p.S) wis[nw++] = wi1;
+    const size_t zplane = (size_t)p.S * p.S;
+    for (int c = 0; c < p.C; ++c) {
+        float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b) {
+                const int u = Y - his[a] * p.step_out, v = X - wis[b] * p.step_out;
+                const size_t t = (size_t)his[a] * p.w_blocks + wis[b];
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.z + (t * p.C + c) * zplane + (size_t)u * p.S + v));
+                const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                const float zv[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (p.blend > 0) {
+                        const float w = blend_weight(p, u, v + k);
+                        num[k] += w * zv[k];
+                        den[k] += w;
+                    } else {
+                        num[k] = zv[k];
+                        den[k] = 1.f;
+                    }
+                }
+            }
+        *reinterpret_cast<float4*>(p.out + ((size_t)c * p.y_h + Y) * p.y_w + X) =
+            make_float4(clamp01(num[0] / den[0]), clamp01(num[1] / den[1]), clamp01(num[2] / den[2]), clamp01(num[3] / den[3]));
+    }
+}
+
 }  // namespace nb200
 
 using namespace nb200;
@@ -147,7 +188,10 @@ extern "C" int nb200_tile_gather_blend(const void* z_all, int C, const nb200_til
         p.ring[d] = (float)(1.0 - (1.0 / (blend_size + 1)) * (i + 1));
     }
     ProfScope ps((cudaStream_t)stream, PC_BLEND, (double)C * p.y_h * p.y_w * 4 + (double)p.h_blocks * p.w_blocks * C * p.S * p.S * 2);
-    tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
+    if (p.y_w % 4 == 0 && p.step_out % 4 == 0 && p.S % 4 == 0 && ((uintptr_t)out & 15) == 0)
+        tile_gather_blend4_kernel<<<dim3(cdiv(p.y_w / 4, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
+    else
+        tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
     NB_LAUNCHED();
     return 0;
 }

@@ -260,12 +260,46 @@ __global__ void __launch_bounds__(256) to_image_kernel(const __half* __restrict_
     z[i] = __float2half_rn(v);
 }
 
+// r=4, down=1 fast path: one thread per token reads its 48 contiguous channels (6 x 16 B) and writes, for each
+// colour plane, four rows of four horizontally adjacent pixels (8-byte stores, coalesced across the warp).
+__global__ void __launch_bounds__(256) to_image_r4_kernel(const __half* __restrict__ y, __half* __restrict__ z, int n, int Hs, int Ws) {
+    const size_t total = (size_t)n * Hs * Ws;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int tx = (int)(i % Ws), ty = (int)((i / Ws) % Hs), b = (int)(i / ((size_t)Ws * Hs));
+    const uint4* src = reinterpret_cast<const uint4*>(y + i * 48);
+    const int S = Hs * 4;
+    const __half2 zero = __float2half2_rn(0.f), one = __float2half2_rn(1.f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // channel index = c*16 + dy*4 + dx (F.pixel_shuffle): two uint4 per colour plane
+        uint4 v0 = __ldg(src + 2 * c), v1 = __ldg(src + 2 * c + 1);
+        __half2* h0 = reinterpret_cast<__half2*>(&v0);
+        __half2* h1 = reinterpret_cast<__half2*>(&v1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h0[k] = __hmin2(__hmax2(h0[k], zero), one);  // clamp(z, 0, 1), swin_unet.py:286
+            h1[k] = __hmin2(__hmax2(h1[k], zero), one);
+        }
+        __half* dst = z + (((size_t)b * 3 + c) * S + (size_t)ty * 4) * S + (size_t)tx * 4;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(v0.x, v0.y);
+        *reinterpret_cast<uint2*>(dst + S) = make_uint2(v0.z, v0.w);
+        *reinterpret_cast<uint2*>(dst + 2 * (size_t)S) = make_uint2(v1.x, v1.y);
+        *reinterpret_cast<uint2*>(dst + 3 * (size_t)S) = make_uint2(v1.z, v1.w);
+    }
+}
+
 int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws, int cs, int r, int down) {
     NB_CHECK(down == 1 || down == 2 || down == 4, "downscale must be 1, 2 or 4");
     NB_CHECK(Hs == Ws && (Hs * r) % down == 0, "bad ToImage geometry");
     const size_t total = (size_t)n * 3 * (Hs * r / down) * (Ws * r / down);
     ProfScope ps(st, PC_TOIMG, (double)n * Hs * Ws * cs * 2 + (double)total * 2);
-    to_image_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(y, z, n, Hs, Ws, cs, r, down);
+    if (r == 4 && down == 1 && cs == 48) {
+        const size_t tokens = (size_t)n * Hs * Ws;
+        to_image_r4_kernel<<<(unsigned)cdiv64(tokens, 256), 256, 0, st>>>(y, z, n, Hs, Ws);
+    } else {
+        to_image_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(y, z, n, Hs, Ws, cs, r, down);
+    }
     NB_LAUNCHED();
     return 0;
 }
