@@ -174,7 +174,8 @@ int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci, int Cin, i
 
 /* shifted-window attention core between the qkv and proj Linears
  * (torchvision swin_transformer.py:166-221), window 6x6, 6 heads.
- * qkv [B][H][W][3C] fp16 -> out [B][H][W][C] fp16; bias_table fp32 [121][6]. */
+ * qkv: three dense planes q | k | v, each [B][H][W][C] fp16 (how the engine's qkv GEMM writes them)
+ * -> out [B][H][W][C] fp16; bias_table fp32 [121][6]. */
 int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B,
                                int H, int W, int C, int heads, int shift, void* stream);
 

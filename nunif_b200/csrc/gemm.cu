@@ -172,9 +172,12 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         case CG_LINEAR_FLAT: {
             const long long M = (long long)g.B * g.Hi * g.Wi;
             p.B = 1; p.Ho = 1; p.Wo = (int)M; p.TH = 1; p.TW = 128;
-            p.taps = 1; ktap = g.Cin;
-            dims[0] = g.Cin; dims[1] = M; dims[2] = 1; dims[3] = 1; dims[4] = 1;
-            strides[0] = g.Ci * e; strides[1] = M * g.Ci * e; strides[2] = strides[1]; strides[3] = strides[1];
+            p.taps = g.a_planes; ktap = g.Cin;
+            NB_CHECK(g.a_planes >= 1 && g.a_planes <= 16, "bad plane count");
+            for (int t = 0; t < p.taps; ++t) { p.tap_dy[t] = 0; p.tap_dx[t] = 0; p.tap_dyi[t] = (int8_t)t; }
+            dims[0] = g.Cin; dims[1] = M; dims[2] = g.a_planes; dims[3] = 1; dims[4] = 1;
+            strides[0] = g.Ci * e; strides[1] = (g.a_planes > 1 ? (cuuint64_t)g.a_plane_stride : (cuuint64_t)M * g.Ci) * e;
+            strides[2] = (cuuint64_t)M * g.Ci * e * g.a_planes; strides[3] = strides[2];
             break;
         }
         case CG_LINEAR_2D:
@@ -211,6 +214,11 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     p.has_res = g.res ? 1 : 0;
     p.res_before_act = g.res_before_act;
     const bool shuf = g.out_mode == OUT_PIXSHUF2;
+    const bool split = g.out_mode == OUT_SPLIT;
+    if (split) {
+        NB_CHECK(g.cout % 16 == 0 && g.N % g.cout == 0 && g.N / g.cout <= 4, "split output: N must be 1..4 blocks of cout");
+        NB_CHECK(!g.res, "split output does not take a residual");
+    }
     if (shuf) {
         NB_CHECK(g.kind != CG_LINEAR_FLAT, "pixel-shuffle output needs 2-D tiling");
         NB_CHECK(g.cout % 16 == 0 && g.N == 4 * g.cout, "pixel-shuffle: N must be 4*cout, cout % 16 == 0");
@@ -222,7 +230,7 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
         for (int c : cands) {
             const int w = (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : 16);
-            if (g.N % c == 0 && (!shuf || g.cout % w == 0)) { bn = c; cw = w; break; }
+            if (g.N % c == 0 && (!shuf || g.cout % w == 0) && (!split || g.cout % c == 0)) { bn = c; cw = w; break; }
         }
     }
     NB_CHECK(bn > 0, "no BLOCK_N divides N");
@@ -237,7 +245,11 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     cuuint32_t bbox[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
     if (encode(&maps.b, g.Wt, 2, bdims, bstr, bbox, BK * 2)) return 1;
     // ---- output / residual views
-    if (!shuf) {
+    if (split) {
+        for (int q = 0; q < g.N / g.cout; ++q)
+            if (encode_nhwc4(&maps.o[q], g.out + (size_t)q * g.split_stride, g.cout, p.Wo, p.Ho, p.B, g.ldo, (long long)p.Wo * g.ldo,
+                             (long long)p.Ho * p.Wo * g.ldo, cw, p.TW, p.TH)) return 1;
+    } else if (!shuf) {
         if (encode_nhwc4(&maps.o[0], g.out, g.N, p.Wo, p.Ho, p.B, g.ldo, (long long)p.Wo * g.ldo, (long long)p.Ho * p.Wo * g.ldo,
                          cw, p.TW, p.TH)) return 1;
         if (g.res) {

@@ -20,7 +20,10 @@ struct ConvGemm {
     int act = 0;
     __half* out = nullptr;      // NHWC fp16, channel stride ldo
     int ldo = 0;
-    int out_mode = 0, cout = 0; // OUT_PIXSHUF2: N = 4*cout ordered (dy, dx, co)
+    int out_mode = 0, cout = 0; // OUT_PIXSHUF2: N = 4*cout ordered (dy, dx, co); OUT_SPLIT: N = nsplit*cout
+    long long split_stride = 0; // OUT_SPLIT: elements between the dense [M][cout] output planes
+    int a_planes = 1;           // CG_LINEAR_FLAT: A is `a_planes` dense [M][Cin] planes (K = a_planes*Cin, plane-major)
+    long long a_plane_stride = 0;
     const __half* res = nullptr;
     int ldr = 0, res_H = 0, res_W = 0, res_cy = 0, res_cx = 0, res_before_act = 0;
 };

@@ -9,7 +9,7 @@
 //       - the CTAs that share an activation tile (n_tiles of them) run in lock-step => the re-read hits L2;
 //   * an A ring (TMA producer warp -> MMA warp) that runs ahead across tile boundaries;
 //   * two TMEM accumulators (2 x BLOCK_N columns): the MMA of tile j+1 overlaps the epilogue of tile j;
-//   * 8 epilogue warps; results go through a ring of 128B-swizzled staging chunks and leave with TMA
+//   * 16 epilogue warps; results go through a ring of 128B-swizzled staging chunks and leave with TMA
 //     tensor stores (the leader only ever waits for the store issued PG_NOUT chunks earlier); residual tiles
 //     are TMA-prefetched by the producer into their own ring, PG_NRES chunks ahead of the epilogue.
 // Every global access is a bulk tensor copy; the kernel is designed to sit on the HBM roofline for the
@@ -22,7 +22,8 @@ namespace nb200 {
 constexpr int PG_MAX_STAGES = 8;   // A(/B) ring depth upper bound
 constexpr int PG_NOUT = 3;         // output staging ring (chunks of [128][CW] fp16 waiting for their TMA store)
 constexpr int PG_NRES = 3;         // residual prefetch ring (same chunk shape), only allocated when a residual exists
-constexpr int PG_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int PG_EPI_WARPS = 16;   // four warps per TMEM lane group: enough warps in flight to hide the tcgen05.ld / MUFU latency
+constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
 
 struct PersistParams {
     GemmParams g;
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                         const int buf = cq % PG_NRES;
                         mbar_wait(&res_empty[buf], ((cq / PG_NRES) & 1) ^ 1);
                         const int n = n0 + c * CW;
-                        const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
-                        const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
+                        const int g = p.out_mode != OUT_NHWC ? n / p.cout : 0;
+                        const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
                         mbar_expect_tx(&res_full[buf], CH_BYTES);
                         tma_load_4d(&maps.r[g], &res_full[buf], sRes + buf * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
                     }
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue (warps 2..17) =====================
         const int lane_grp = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;   // which 16-column blocks of a chunk this warp converts
         const int r = lane_grp * 32 + lane;
         const bool leader = (warp == 2 && lane == 0);
         const int act = p.act;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                 uint8_t* bufp = sOut + buf * CH_BYTES;
                 const uint8_t* resp = sRes + rbuf * CH_BYTES;
 #pragma unroll 1
-                for (int sub = half; sub < CW / 16; sub += 2) {
+                for (int sub = part; sub < CW / 16; sub += PG_EPI_WARPS / 4) {
                     uint32_t acc[16];
                     tmem_ld16(trow + c * CW + sub * 16, acc);
                     tmem_ld_wait();
@@ -237,13 +238,13 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                 }
                 if (c == NCH - 1) tc_fence_before();  // this tile's TMEM reads are done before the barrier below
                 fence_async_smem();
-                epi_bar_sync();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * PG_EPI_WARPS) : "memory");
                 if (leader) {
                     if (c == NCH - 1) mbar_arrive(&acc_empty[a]);  // hand the accumulator back to the MMA warp
                     if (has_res) mbar_arrive(&res_empty[rbuf]);    // residual chunk consumed by every epilogue thread
                     const int n = n0 + c * CW;
-                    const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
-                    const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
+                    const int g = p.out_mode != OUT_NHWC ? n / p.cout : 0;
+                    const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
                     tma_store_4d(&maps.o[g], bufp, co, x0, y0, b);
                     tma_store_commit();
                     // all but the PG_NOUT-1 newest stores have read their staging buffers: hand those buffers back.

@@ -25,7 +25,7 @@
 namespace nb200 {
 
 enum : int { ACT_NONE = 0, ACT_LRELU01 = 1, ACT_GELU = 2, ACT_RELU = 3 };
-enum : int { OUT_NHWC = 0, OUT_PIXSHUF2 = 1 };
+enum : int { OUT_NHWC = 0, OUT_PIXSHUF2 = 1, OUT_SPLIT = 2 };
 
 struct GemmParams {
     // output tiling: the M dimension is (b, y, x) over Ho x Wo pixels, tiled TH x TW (TH*TW == 128)
@@ -38,6 +38,7 @@ struct GemmParams {
     const float* bias;   // [N] or null
     int act;
     int out_mode, cout;  // OUT_PIXSHUF2: N = 4*cout ordered (dy,dx,co); maps o[g]/r[g] are the stride-2 views
+                         // OUT_SPLIT: N = nsplit*cout, block g goes to its own dense [M][cout] plane (maps o[g])
     int has_res, res_cy, res_cx;
     int res_before_act;  // 0: out = act(acc+bias) + res ; 1: out = act(acc+bias+res)
 };
@@ -195,7 +196,7 @@ __device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
     }
 }
 
-constexpr int GEMM_EPI_WARPS = 8;                       // two warps per TMEM lane group, each takes every other 16-column block
+constexpr int GEMM_EPI_WARPS = 8;                       // non-persistent kernel: two warps per TMEM lane group
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 template <int BLOCK_N, int BK>
@@ -317,8 +318,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
 #pragma unroll 1
                 for (int c = 0; c < Cfg::NCH; ++c) {
                     const int n = n0 + c * CW;
-                    const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
-                    const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
+                    const int g = p.out_mode != OUT_NHWC ? n / p.cout : 0;
+                    const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
                     tma_load_4d(&maps.r[g], res_bar, stg + c * Cfg::CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
                 }
             }
@@ -385,8 +386,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_conv_kernel(const __grid_co
 #pragma unroll 1
             for (int c = 0; c < Cfg::NCH; ++c) {
                 const int n = n0 + c * CW;
-                const int g = p.out_mode == OUT_PIXSHUF2 ? n / p.cout : 0;
-                const int co = p.out_mode == OUT_PIXSHUF2 ? n - g * p.cout : n;
+                const int g = p.out_mode != OUT_NHWC ? n / p.cout : 0;
+                const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
                 // out-of-range rows/cols of edge tiles are clipped by TMA
                 tma_store_4d(&maps.o[g], stg + c * Cfg::CH_BYTES, co, x0, y0, b);
             }

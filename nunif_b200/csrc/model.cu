@@ -286,12 +286,15 @@ struct Arena {
     }
 };
 
+// split > 0: the N outputs are written as N/split dense [M][split] planes (OUT_SPLIT); a_planes > 1: A is given as planes
 static int linear_flat(cudaStream_t st, const nb200_model* m, const Lin& l, const __half* A, long long M, int lda, __half* out,
-                       int ldo, int act, const __half* res = nullptr, int ldr = 0) {
+                       int ldo, int act, const __half* res = nullptr, int ldr = 0, int split = 0, int a_planes = 1) {
     ConvGemm g;
-    g.A = A; g.B = 1; g.Hi = 1; g.Wi = (int)M; g.Ci = lda; g.Cin = l.K; g.kind = CG_LINEAR_FLAT;
+    g.A = A; g.B = 1; g.Hi = 1; g.Wi = (int)M; g.Ci = lda; g.Cin = l.K / a_planes; g.kind = CG_LINEAR_FLAT;
+    g.a_planes = a_planes; g.a_plane_stride = (long long)M * lda;
     g.Wt = m->at<__half>(l.w); g.N = l.N; g.bias = m->at<float>(l.b); g.act = act; g.out = out; g.ldo = ldo;
     g.res = res; g.ldr = ldr;
+    if (split) { g.out_mode = OUT_SPLIT; g.cout = split; g.split_stride = (long long)M * split; g.ldo = split; }
     return conv_gemm(st, g);
 }
 
@@ -299,11 +302,19 @@ static int swin_block(cudaStream_t st, const nb200_model* m, const SwinBlockW& w
                       __half* HID) {
     const int C = w.C;
     const long long T = (long long)n * H * H;
-    if (linear_flat(st, m, w.qkv, X, T, C, QKV, 3 * C, ACT_NONE)) return 1;
-    if (window_attention(st, QKV, m->at<float>(w.table), ATT, n, H, H, C, w.shift)) return 1;
+    // q | k | v are written as three dense [T][C] planes: every CTA stores whole contiguous rows, and the
+    // attention kernel reads each matrix with unit stride
+    if (linear_flat(st, m, w.qkv, X, T, C, QKV, C, ACT_NONE, nullptr, 0, /*split=*/C)) return 1;
+    if (window_attention(st, QKV, m->at<float>(w.table), ATT, n, H, H, C, w.shift, (size_t)T * C)) return 1;
     if (linear_flat(st, m, w.proj, ATT, T, C, X, C, ACT_NONE, X, C)) return 1;       // x = x + attn(x)   :453
-    if (linear_flat(st, m, w.fc1, X, T, C, HID, 2 * C, ACT_GELU)) return 1;
-    if (linear_flat(st, m, w.fc2, HID, T, 2 * C, X, C, ACT_NONE, X, C)) return 1;    // x = x + mlp(x)    :454
+    if (C == 192) {
+        // hidden = 2 planes of [T][192] (same reason); fc2 consumes them as two K-taps
+        if (linear_flat(st, m, w.fc1, X, T, C, HID, C, ACT_GELU, nullptr, 0, /*split=*/C)) return 1;
+        if (linear_flat(st, m, w.fc2, HID, T, C, X, C, ACT_NONE, X, C, 0, /*a_planes=*/2)) return 1;  // x = x + mlp(x) :454
+    } else {
+        if (linear_flat(st, m, w.fc1, X, T, C, HID, 2 * C, ACT_GELU)) return 1;
+        if (linear_flat(st, m, w.fc2, HID, T, 2 * C, X, C, ACT_NONE, X, C)) return 1;
+    }
     return 0;
 }
 

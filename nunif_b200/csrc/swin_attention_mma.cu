@@ -45,7 +45,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 
 template <int D>
 __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
-                                                                   __half* __restrict__ out, int H, int W, int shift) {
+                                                                   __half* __restrict__ out, int H, int W, int shift,
+                                                                   size_t plane) {
     constexpr int C = D * HEADS;
     constexpr int LD = C + 8;  // padded row: (C+8)*2 bytes = 4 words mod 32 banks -> conflict-free fragment loads
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -73,13 +74,13 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
         sreg[tid] = reg;
     }
     __syncthreads();
-    // ---- stage q, k, v: one token row = 3C contiguous halves in global, 16-byte cp.async each
+    // ---- stage q, k, v: three dense [T][C] planes (the qkv GEMM writes them split, OUT_SPLIT), 16-byte cp.async each
     constexpr int VPT = C / 8;
     for (int i = tid; i < WTOK * 3 * VPT; i += blockDim.x) {
         const int t = i / (3 * VPT), v = i - t * (3 * VPT);
         const int m = v / VPT, vv = v - m * VPT;  // m: 0 = q, 1 = k, 2 = v
         __half* dst = (m == 0 ? sq : (m == 1 ? sk : sv)) + t * LD + vv * 8;
-        cp_async16(dst, qkv + (size_t)stok[t] * (3 * C) + v * 8);
+        cp_async16(dst, qkv + (size_t)m * plane + (size_t)stok[t] * C + vv * 8);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -255,7 +256,7 @@ static size_t attn_smem_bytes() {
 }
 
 int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_f, __half* out, int B, int H, int W, int C,
-                     int shift) {
+                     int shift, size_t plane) {
     const float4* bias_table = reinterpret_cast<const float4*>(bias_frag_f);
     NB_CHECK(H % WS == 0 && W % WS == 0, "feature map must be a multiple of the 6x6 window");
     NB_CHECK(C == 96 || C == 192, "window attention supports C=96 (d=16) and C=192 (d=32)");
@@ -269,7 +270,7 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_
             NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             cfg = true;
         }
-        window_attention_mma_kernel<16><<<grid, 192, attn_smem_bytes<16>(), st>>>(qkv, bias_table, out, H, W, shift);
+        window_attention_mma_kernel<16><<<grid, 192, attn_smem_bytes<16>(), st>>>(qkv, bias_table, out, H, W, shift, plane);
     } else {
         static bool cfg = false;
         if (!cfg) {
@@ -277,7 +278,7 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_
             NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             cfg = true;
         }
-        window_attention_mma_kernel<32><<<grid, 192, attn_smem_bytes<32>(), st>>>(qkv, bias_table, out, H, W, shift);
+        window_attention_mma_kernel<32><<<grid, 192, attn_smem_bytes<32>(), st>>>(qkv, bias_table, out, H, W, shift, plane);
     }
     NB_LAUNCHED();
     return 0;

@@ -316,7 +316,7 @@ extern "C" int nb200_window_attention_f16(const void* qkv, const float* bias_tab
     float* frag = nullptr;
     NB_CUDA(cudaMallocAsync((void**)&frag, BIAS_FRAG_FLOATS * sizeof(float), st));
     int rc = build_bias_frag(st, bias_table, frag);
-    if (!rc) rc = window_attention(st, (const __half*)qkv, frag, (__half*)out, B, H, W, C, shift);
+    if (!rc) rc = window_attention(st, (const __half*)qkv, frag, (__half*)out, B, H, W, C, shift, (size_t)B * H * W * C);
     cudaFreeAsync(frag, st);
     return rc;
 }

@@ -6,7 +6,8 @@ int stem_conv3x3(cudaStream_t st, const __half* x, const float* wt, const float*
                  int cout_pad, int ldo);
 constexpr int BIAS_FRAG_FLOATS = 6 * 3 * 6 * 32 * 4;  // per Swin block, see swin_attention_mma.cu
 int build_bias_frag(cudaStream_t st, const float* table_121x6, float* frag);
+// qkv: three dense planes q | k | v, each [B][H][W][C], `plane` elements apart
 int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag, __half* out, int B, int H, int W, int C,
-                     int shift);
+                     int shift, size_t plane);
 int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws, int cs, int r, int down);
 }  // namespace nb200

@@ -112,7 +112,8 @@ def test_window_attention_core(B, H, W, C, shift):
     qkv = torch.randn(B, H, W, 3 * C, generator=g).half().to(DEV)
     table = (torch.randn(121, heads, generator=g) * 0.5).to(DEV)
     out = torch.full((B, H, W, C), 9.0, dtype=torch.float16, device=DEV)
-    _lib.check(_lib.lib().nb200_window_attention_f16(_lib.ptr(qkv), _lib.ptr(table), _lib.ptr(out), B, H, W, C, heads, shift,
+    planes = qkv.view(B, H, W, 3, C).permute(3, 0, 1, 2, 4).contiguous()   # q | k | v as three dense [B,H,W,C] planes
+    _lib.check(_lib.lib().nb200_window_attention_f16(_lib.ptr(planes), _lib.ptr(table), _lib.ptr(out), B, H, W, C, heads, shift,
                                                      _lib.stream_ptr()))
     torch.cuda.synchronize()
     from nunif_b200.synth import relative_position_index
