@@ -131,6 +131,45 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
+    """Secondary numbers (BASELINE.json configs[2], post-depth stages only - the DepthAnything body is not part of this
+    round): dilate_edge[2,1] + per-frame min/max + warp + SBS compose on B 1080p frames resident in HBM, device-timed.
+    Algorithmic bytes per frame: (3 in + 6 out planes) * 4 B * H*W + the depth map = 75.7 MB."""
+    import ctypes
+    import torch
+    from nunif_b200 import synth, _lib
+    from nunif_b200.iw3 import stereo_sbs
+    H, W, h, w = 1080, 1920, 392, 686
+    c = torch.stack([synth.synth_image(50 + i, 3, H, W, smooth=False) for i in range(B)]).to(dev)
+    d = synth.synth_depth(60, B, h, w).to(dev) * 7.0 + 0.5
+    out = {}
+    for method in ("forward_fill", "backward"):
+        for _ in range(3):
+            y = stereo_sbs(c, d, 2.0, 0.5, method=method, edge_dilation=[2, 1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            y = stereo_sbs(c, d, 2.0, 0.5, method=method, edge_dilation=[2, 1])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        _lib.check(lib.nb200_profile_enable(1))
+        y = stereo_sbs(c, d, 2.0, 0.5, method=method, edge_dilation=[2, 1])
+        buf = ctypes.create_string_buffer(8192)
+        _lib.check(lib.nb200_profile_report(buf, 8192))
+        _lib.check(lib.nb200_profile_enable(0))
+        prof = json.loads(buf.value.decode())
+        k = prof.get("forward_warp" if method == "forward_fill" else "backward_warp", {"ms": 0, "work": 0})
+        gbs = k["work"] / (k["ms"] / 1e3) / 1e9 if k["ms"] > 0 else 0.0
+        out[method] = {"fps": B / (ms / 1e3), "ms_per_batch": ms, "batch": B,
+                       "warp_kernel_ms": k["ms"], "warp_kernel_GBps_algorithmic": gbs, "warp_frac_of_hbm_peak": gbs / peaks_gbs,
+                       "kernel_classes_ms": {kk: round(v["ms"], 4) for kk, v in prof.items()}}
+        del y
+    out["note"] = "post-depth stages only (dilate_edge [2,1], minmax, warp, SBS); depth network not included"
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -209,6 +248,8 @@ def run_b200(args):
         prof = json.loads(buf.value.decode())
         del y
 
+        iw3 = bench_iw3(dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if rank == 0 else None
+
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -244,6 +285,8 @@ def run_b200(args):
                      "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None, "traffic": None},
         "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }
+    if iw3 is not None:
+        line["iw3_1080p"] = iw3
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cores = host_cores()

@@ -107,7 +107,8 @@ static int launch_persistent_t(cudaStream_t st, const GemmMaps& maps, const Gemm
     pp.grid_m = grid_m;
     const int grid = grid_m * p.n_tiles;
     constexpr int b_chunk = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
-    const int stg = (PG_NOUT + (p.has_res ? PG_NRES : 0)) * Cfg::CH_BYTES;
+    pp.nout = p.has_res ? 3 : 4;
+    const int stg = (pp.nout + (p.has_res ? PG_NRES : 0)) * Cfg::CH_BYTES + BN * 4 /*bias*/;
     // weights resident in shared memory when they fit next to >= 3 activation stages
     const long long bres = (long long)pp.k_iters * b_chunk;
     const long long room_res = (long long)PG_SMEM_BUDGET - stg - bres;

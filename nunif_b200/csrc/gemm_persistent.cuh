@@ -20,7 +20,9 @@
 namespace nb200 {
 
 constexpr int PG_MAX_STAGES = 8;   // A(/B) ring depth upper bound
-constexpr int PG_NOUT = 3;         // output staging ring (chunks of [128][CW] fp16 waiting for their TMA store)
+constexpr int PG_NOUT = 4;         // output staging ring capacity (chunks of [128][CW] fp16 waiting for their TMA store);
+                                   // the host picks 4 (buffer hand-back off the critical path) or 3 (when a residual ring
+                                   // also has to fit)
 constexpr int PG_NRES = 3;         // residual prefetch ring (same chunk shape), only allocated when a residual exists
 constexpr int PG_EPI_WARPS = 16;   // four warps per TMEM lane group: enough warps in flight to hide the tcgen05.ld / MUFU latency
 constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
@@ -31,6 +33,7 @@ struct PersistParams {
     int grid_m;         // CTAs per n-tile (gridDim.x / n_tiles)
     int stages;         // ring depth chosen by the host for the shared-memory budget
     int k_iters;
+    int nout;           // output staging buffers in use (3 or 4)
 };
 
 template <int BLOCK_N, int BK, bool RESIDENT_B>
@@ -42,15 +45,16 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
     constexpr int STAGE_BYTES = RESIDENT_B ? A_BYTES : A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     const GemmParams& p = pp.g;
-    const int SA = pp.stages, k_iters = pp.k_iters;
+    const int SA = pp.stages, k_iters = pp.k_iters, NOUT = pp.nout;
 
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;                                               // resident weights: k_iters chunks of B_BYTES
     uint8_t* sRing = sB + (RESIDENT_B ? k_iters * B_BYTES : 0);       // SA stages
     uint8_t* sOut = sRing + SA * STAGE_BYTES;                         // PG_NOUT output staging chunks
-    uint8_t* sRes = sOut + PG_NOUT * CH_BYTES;                        // PG_NRES residual chunks (if has_res)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (p.has_res ? PG_NRES * CH_BYTES : 0));
+    uint8_t* sRes = sOut + NOUT * CH_BYTES;                           // PG_NRES residual chunks (if has_res)
+    float* sBias = reinterpret_cast<float*>(sRes + (p.has_res ? PG_NRES * CH_BYTES : 0));  // this CTA's BLOCK_N biases
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BLOCK_N);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + PG_MAX_STAGES;
     uint64_t* acc_full = a_empty + PG_MAX_STAGES;
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + BLOCK_N) sBias[threadIdx.x - 64] = p.bias ? __ldg(p.bias + n0 + (threadIdx.x - 64)) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -180,8 +185,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c, ++cq) {
-                const int buf = cq % PG_NOUT, rbuf = cq % PG_NRES;
-                mbar_wait(&out_empty[buf], ((cq / PG_NOUT) & 1) ^ 1);     // the store issued PG_NOUT chunks ago has read this buffer
+                const int buf = cq % NOUT, rbuf = cq % PG_NRES;
+                mbar_wait(&out_empty[buf], ((cq / NOUT) & 1) ^ 1);        // the store issued NOUT chunks ago has read this buffer
                 if (has_res) mbar_wait(&res_full[rbuf], (cq / PG_NRES) & 1);  // residual chunk landed
                 uint8_t* bufp = sOut + buf * CH_BYTES;
                 const uint8_t* resp = sRes + rbuf * CH_BYTES;
@@ -194,19 +199,16 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                     uint4* s0 = reinterpret_cast<uint4*>(bufp + o0);
                     uint4* s1 = reinterpret_cast<uint4*>(bufp + o1);
                     float v[16];
-                    if (p.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c * CW + sub * 16);
+                    {
+                        const float4* bp = reinterpret_cast<const float4*>(sBias + c * CW + sub * 16);  // smem broadcast
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 bq = __ldg(bp + q);
+                            const float4 bq = bp[q];
                             v[4 * q] = __uint_as_float(acc[4 * q]) + bq.x;
                             v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + bq.y;
                             v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + bq.z;
                             v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + bq.w;
                         }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
                     }
                     if (has_res) {
                         float rv[16];
@@ -247,11 +249,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                     const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
                     tma_store_4d(&maps.o[g], bufp, co, x0, y0, b);
                     tma_store_commit();
-                    // all but the PG_NOUT-1 newest stores have read their staging buffers: hand those buffers back.
-                    // The next chunk needs exactly the oldest of them, so this wait is (almost) never blocking.
-                    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PG_NOUT - 1) : "memory");
-                    while (released + (PG_NOUT - 1) <= cq) {
-                        mbar_arrive(&out_empty[released % PG_NOUT]);
+                    // all but the 2 newest stores have read their staging buffers: hand those buffers back.  With 4
+                    // buffers the next chunk's buffer was already handed back one chunk earlier (off the critical path).
+                    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                    while (released + 2 <= cq) {
+                        mbar_arrive(&out_empty[released % NOUT]);
                         ++released;
                     }
                 }
