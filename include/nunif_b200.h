@@ -182,6 +182,7 @@ int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* o
 /* Kernel-class device timing (CUDA events around every launch of this library) used by
  * bench.py for the live roofline figure.  report writes a JSON object
  * {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...} and synchronises the device. */
+int nb200_tune_set(int key, int value);   /* GEMM scheduling knobs for profiles/gemm_bench.py */
 int nb200_profile_enable(int on);
 int nb200_profile_report(char* buf, size_t cap);
 

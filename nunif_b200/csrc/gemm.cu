@@ -81,6 +81,9 @@ static int num_sms() {
 
 constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
 
+// tuning knobs for profiles/gemm_bench.py (nb200_tune_set); defaults are the shipped configuration
+int g_tune[8] = {/*0 nout without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, 0, 0, 0, 0, 0};
+
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {
     static int configured = 0;  // per instantiation: largest size configured so far
@@ -101,20 +104,20 @@ static int launch_persistent_t(cudaStream_t st, const GemmMaps& maps, const Gemm
     pp.g = p;
     pp.m_tiles = m_tiles;
     pp.k_iters = p.taps * p.cpt;
-    int grid_m = num_sms() / p.n_tiles;
+    int grid_m = (g_tune[2] > 0 ? g_tune[2] : num_sms()) / p.n_tiles;
     if (grid_m < 1) grid_m = 1;
     if (grid_m > m_tiles) grid_m = m_tiles;
     pp.grid_m = grid_m;
     const int grid = grid_m * p.n_tiles;
     constexpr int b_chunk = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
-    pp.nout = p.has_res ? 3 : 4;
+    pp.nout = p.has_res ? 3 : g_tune[0];
     const int stg = (pp.nout + (p.has_res ? PG_NRES : 0)) * Cfg::CH_BYTES + BN * 4 /*bias*/;
     // weights resident in shared memory when they fit next to >= 3 activation stages
     const long long bres = (long long)pp.k_iters * b_chunk;
     const long long room_res = (long long)PG_SMEM_BUDGET - stg - bres;
     if (room_res >= 3LL * Cfg::A_BYTES) {
         int stages = (int)(room_res / Cfg::A_BYTES);
-        if (stages > PG_MAX_STAGES) stages = PG_MAX_STAGES;
+        if (stages > g_tune[1]) stages = g_tune[1];
         const size_t smem = (size_t)bres + (size_t)stages * Cfg::A_BYTES + stg + 1024 + 512;
         return launch_p<BN, BK, true>(st, maps, pp, stages, smem, grid);
     }
@@ -298,4 +301,11 @@ extern "C" int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci,
     g.out_mode = out_mode; g.cout = cout; g.res = (const __half*)res; g.ldr = ldr; g.res_H = res_H; g.res_W = res_W;
     g.res_cy = res_cy; g.res_cx = res_cx; g.res_before_act = res_before_act;
     return conv_gemm((cudaStream_t)stream, g);
+}
+
+// profiling knobs (see g_tune in this file); not part of the reference-facing API
+extern "C" int nb200_tune_set(int key, int value) {
+    NB_CHECK(key >= 0 && key < 8, "bad key");
+    g_tune[key] = value;
+    return 0;
 }

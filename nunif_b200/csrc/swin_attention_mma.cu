@@ -74,13 +74,17 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
         sreg[tid] = reg;
     }
     __syncthreads();
-    // ---- stage q, k, v: three dense [T][C] planes (the qkv GEMM writes them split, OUT_SPLIT), 16-byte cp.async each
-    constexpr int VPT = C / 8;
-    for (int i = tid; i < WTOK * 3 * VPT; i += blockDim.x) {
-        const int t = i / (3 * VPT), v = i - t * (3 * VPT);
-        const int m = v / VPT, vv = v - m * VPT;  // m: 0 = q, 1 = k, 2 = v
-        __half* dst = (m == 0 ? sq : (m == 1 ? sk : sv)) + t * LD + vv * 8;
-        cp_async16(dst, qkv + (size_t)m * plane + (size_t)stok[t] * C + vv * 8);
+    // ---- stage q, k, v: three dense [T][C] planes (the qkv GEMM writes them split, OUT_SPLIT), 16-byte cp.async each.
+    // thread -> (16-byte column vv, row group rg); it walks tokens rg, rg+RG, ... of all three planes
+    constexpr int VPT = C / 8;         // 16-byte columns per token row: 24 (C=192) or 12 (C=96)
+    constexpr int RG = 192 / VPT;      // 8 or 16 row groups
+    const int vv = tid % VPT, rg = tid / VPT;
+    for (int t = rg; t < WTOK; t += RG) {
+        const __half* src = qkv + (size_t)stok[t] * C + vv * 8;
+        __half* dst = sq + t * LD + vv * 8;
+        cp_async16(dst, src);
+        cp_async16(dst + WTOK * LD, src + plane);
+        cp_async16(dst + 2 * WTOK * LD, src + 2 * plane);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -158,6 +162,12 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
     for (int mt = 0; mt < 3; ++mt) {
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
+            if (mt == 2 && hlf == 1) {  // rows 40..47 never exist: keep P = 0 so they cost nothing downstream
+#pragma unroll
+                for (int nt = 0; nt < 6; ++nt) s[mt][nt][2] = s[mt][nt][3] = 0.f;
+                inv_sum[mt][hlf] = 0.f;
+                continue;
+            }
             float mx = -1e30f;
 #pragma unroll
             for (int nt = 0; nt < 6; ++nt) mx = fmaxf(mx, fmaxf(s[mt][nt][2 * hlf], s[mt][nt][2 * hlf + 1]));
@@ -215,10 +225,8 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
             if (r1 < WTOK) *reinterpret_cast<uint32_t*>(sq + r1 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[mt][nt][2], o[mt][nt][3]);
         }
     __syncthreads();
-    for (int i = tid; i < WTOK * VPT; i += blockDim.x) {
-        const int t = i / VPT, v = i - t * VPT;
-        *reinterpret_cast<uint4*>(out + (size_t)stok[t] * C + v * 8) = *reinterpret_cast<const uint4*>(sq + t * LD + v * 8);
-    }
+    for (int t = rg; t < WTOK; t += RG)
+        *reinterpret_cast<uint4*>(out + (size_t)stok[t] * C + vv * 8) = *reinterpret_cast<const uint4*>(sq + t * LD + vv * 8);
 }
 
 // bias_frag[head][mt][nt][lane] (float4 = accumulator fragment order) = log2(e) * table[rel_index(row, col)][head];
