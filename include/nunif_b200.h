@@ -183,6 +183,7 @@ int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* o
  * bench.py for the live roofline figure.  report writes a JSON object
  * {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...} and synchronises the device. */
 int nb200_tune_set(int key, int value);   /* GEMM scheduling knobs for profiles/gemm_bench.py */
+int nb200_debug_timeline(void* dev_buf);  /* per-role clock64 timeline of CTA 0 (profiles/gemm_timeline.py) */
 int nb200_profile_enable(int on);
 int nb200_profile_report(char* buf, size_t cap);
 

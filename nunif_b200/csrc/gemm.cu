@@ -82,7 +82,8 @@ static int num_sms() {
 constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
 
 // tuning knobs for profiles/gemm_bench.py (nb200_tune_set); defaults are the shipped configuration
-int g_tune[8] = {/*0 nout without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, 0, 0, 0, 0, 0};
+unsigned long long* g_timeline = nullptr;
+int g_tune[8] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, 0, 0, 0, 0, 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {
@@ -110,8 +111,9 @@ static int launch_persistent_t(cudaStream_t st, const GemmMaps& maps, const Gemm
     pp.grid_m = grid_m;
     const int grid = grid_m * p.n_tiles;
     constexpr int b_chunk = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
-    pp.nout = p.has_res ? 3 : g_tune[0];
-    const int stg = (pp.nout + (p.has_res ? PG_NRES : 0)) * Cfg::CH_BYTES + BN * 4 /*bias*/;
+    pp.nq = p.has_res ? 3 : g_tune[0];
+    pp.timeline = g_timeline;
+    const int stg = pp.nq * (p.has_res ? 2 : 1) * Cfg::CH_BYTES + BN * 4 /*bias*/;
     // weights resident in shared memory when they fit next to >= 3 activation stages
     const long long bres = (long long)pp.k_iters * b_chunk;
     const long long room_res = (long long)PG_SMEM_BUDGET - stg - bres;
@@ -301,6 +303,12 @@ extern "C" int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci,
     g.out_mode = out_mode; g.cout = cout; g.res = (const __half*)res; g.ldr = ldr; g.res_H = res_H; g.res_W = res_W;
     g.res_cy = res_cy; g.res_cx = res_cx; g.res_before_act = res_before_act;
     return conv_gemm((cudaStream_t)stream, g);
+}
+
+// debug: device buffer of 4096 u64 that CTA 0 of every following persistent GEMM fills with (event<<56 | clock)
+extern "C" int nb200_debug_timeline(void* dev_buf) {
+    g_timeline = (unsigned long long*)dev_buf;
+    return 0;
 }
 
 // profiling knobs (see g_tune in this file); not part of the reference-facing API

@@ -9,22 +9,25 @@
 //       - the CTAs that share an activation tile (n_tiles of them) run in lock-step => the re-read hits L2;
 //   * an A ring (TMA producer warp -> MMA warp) that runs ahead across tile boundaries;
 //   * two TMEM accumulators (2 x BLOCK_N columns): the MMA of tile j+1 overlaps the epilogue of tile j;
-//   * 16 epilogue warps; results go through a ring of 128B-swizzled staging chunks and leave with TMA
-//     tensor stores (the leader only ever waits for the store issued PG_NOUT chunks earlier); residual tiles
-//     are TMA-prefetched by the producer into their own ring, PG_NRES chunks ahead of the epilogue.
-// Every global access is a bulk tensor copy; the kernel is designed to sit on the HBM roofline for the
-// memory-bound Linears (M x {96,192} activations) and on the tensor roofline for the large-K convs.
+//   * the epilogue is split into independent QUADS (4 warps = the 4 TMEM lane groups).  The CTA's output is a
+//     sequence of [128 x CW] chunks; chunk q goes to quad q mod NQ, which owns one 128B-swizzled staging buffer,
+//     converts the chunk (tcgen05.ld -> bias/activation/residual -> fp16), and issues its own TMA tensor store.
+//     Quads only synchronise internally (128-thread named barriers), so up to NQ chunks are in flight and the
+//     per-chunk latency chain (TMEM load, dependent math, fence, store issue) is overlapped NQ-fold;
+//   * residual chunks are TMA-prefetched by the producer into per-quad buffers, NQ chunks ahead;
+//   * no runtime integer division anywhere in the steady state: ring slots, phases and tile coordinates
+//     advance incrementally (a clock64 timeline of the first version showed ~500-cycle dependent chains of
+//     IDIV/IMOD sequences in every role - profiles/r1/timeline_*.txt).
+// Every global access is a bulk tensor copy.  The Swin Linears (M ~ 1e6, K,N <= 576) are HBM-bound; the
+// traffic-mix floor is max((R+W)/6.6, W/3.9, R/6.2 TB/s) (profiles/r1/hbm_microbench.json).
 #pragma once
 #include "gemm_tcgen05.cuh"
 
 namespace nb200 {
 
 constexpr int PG_MAX_STAGES = 8;   // A(/B) ring depth upper bound
-constexpr int PG_NOUT = 4;         // output staging ring capacity (chunks of [128][CW] fp16 waiting for their TMA store);
-                                   // the host picks 4 (buffer hand-back off the critical path) or 3 (when a residual ring
-                                   // also has to fit)
-constexpr int PG_NRES = 3;         // residual prefetch ring (same chunk shape), only allocated when a residual exists
-constexpr int PG_EPI_WARPS = 16;   // four warps per TMEM lane group: enough warps in flight to hide the tcgen05.ld / MUFU latency
+constexpr int PG_MAX_QUADS = 4;    // epilogue quads (each 4 warps)
+constexpr int PG_EPI_WARPS = 4 * PG_MAX_QUADS;
 constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
 
 struct PersistParams {
@@ -33,44 +36,66 @@ struct PersistParams {
     int grid_m;         // CTAs per n-tile (gridDim.x / n_tiles)
     int stages;         // ring depth chosen by the host for the shared-memory budget
     int k_iters;
-    int nout;           // output staging buffers in use (3 or 4)
+    int nq;             // active epilogue quads == staging buffers (3 with a residual ring, else 4)
+    unsigned long long* timeline;  // optional debug: CTA 0 records (event << 56 | clock) per role (profiles/gemm_timeline.py)
+};
+
+// (tx, ty, b) of a tile index, advanced by a fixed stride without divisions
+struct TileWalk {
+    int tx, ty, b, sx, sy, sb, nx, ny;
+    __device__ __forceinline__ void init(int tile, int stride, int tiles_x, int tiles_y) {
+        nx = tiles_x; ny = tiles_y;
+        tx = tile % tiles_x; ty = (tile / tiles_x) % tiles_y; b = tile / (tiles_x * tiles_y);
+        sx = stride % tiles_x; sy = (stride / tiles_x) % tiles_y; sb = stride / (tiles_x * tiles_y);
+    }
+    __device__ __forceinline__ void step() {
+        tx += sx;
+        int cy = 0;
+        if (tx >= nx) { tx -= nx; cy = 1; }
+        ty += sy + cy;
+        int cb = 0;
+        if (ty >= ny) { ty -= ny; cb = 1; }
+        b += sb + cb;
+    }
 };
 
 template <int BLOCK_N, int BK, bool RESIDENT_B>
 __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __grid_constant__ GemmMaps maps,
                                                                       const __grid_constant__ PersistParams pp) {
     using Cfg = GemmCfg<BLOCK_N, BK>;
-    constexpr int CW = Cfg::CW, NCH = Cfg::NCH, CH_BYTES = Cfg::CH_BYTES;
+    constexpr int CW = Cfg::CW, NCH = Cfg::NCH, CH_BYTES = Cfg::CH_BYTES, NSUB = CW / 16;
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
     constexpr int STAGE_BYTES = RESIDENT_B ? A_BYTES : A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     const GemmParams& p = pp.g;
-    const int SA = pp.stages, k_iters = pp.k_iters, NOUT = pp.nout;
+    const int SA = pp.stages, k_iters = pp.k_iters, NQ = pp.nq;
 
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;                                               // resident weights: k_iters chunks of B_BYTES
     uint8_t* sRing = sB + (RESIDENT_B ? k_iters * B_BYTES : 0);       // SA stages
-    uint8_t* sOut = sRing + SA * STAGE_BYTES;                         // PG_NOUT output staging chunks
-    uint8_t* sRes = sOut + NOUT * CH_BYTES;                           // PG_NRES residual chunks (if has_res)
-    float* sBias = reinterpret_cast<float*>(sRes + (p.has_res ? PG_NRES * CH_BYTES : 0));  // this CTA's BLOCK_N biases
+    uint8_t* sOut = sRing + SA * STAGE_BYTES;                         // NQ output staging chunks (one per quad)
+    uint8_t* sRes = sOut + NQ * CH_BYTES;                             // NQ residual chunks (if has_res)
+    float* sBias = reinterpret_cast<float*>(sRes + (p.has_res ? NQ * CH_BYTES : 0));  // this CTA's BLOCK_N biases
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BLOCK_N);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + PG_MAX_STAGES;
     uint64_t* acc_full = a_empty + PG_MAX_STAGES;
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* res_full = acc_empty + 2;
-    uint64_t* res_empty = res_full + PG_NRES;
-    uint64_t* out_empty = res_empty + PG_NRES;
-    uint64_t* b_full = out_empty + PG_NOUT;
+    uint64_t* res_empty = res_full + PG_MAX_QUADS;
+    uint64_t* b_full = res_empty + PG_MAX_QUADS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // timeline slots: producer [0,1024), MMA [1024,2048), quad-0 leader [2048,3072), quad-1 leader [3072,4096)
+    unsigned long long* tl = (pp.timeline && blockIdx.x == 0) ? pp.timeline : nullptr;
+    int tli = 0;
+#define TL(base, ev) do { if (tl && tli < 1024) { tl[(base) + tli] = ((unsigned long long)(ev) << 56) | (clock64() & 0x00ffffffffffffffull); ++tli; } } while (0)
     const int n_tile = blockIdx.x % p.n_tiles;
     const int m_first = blockIdx.x / p.n_tiles;
     const int n0 = n_tile * BLOCK_N;
     const int my_tiles = m_first < pp.m_tiles ? (pp.m_tiles - m_first + pp.grid_m - 1) / pp.grid_m : 0;
-    const int tiles_xy = p.tiles_x * p.tiles_y;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a);
@@ -82,13 +107,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 1);
+            mbar_init(&acc_empty[s], NCH);   // one arrival per chunk of the tile (from the quad that converted it)
         }
-        for (int s = 0; s < PG_NRES; ++s) {
+        for (int s = 0; s < PG_MAX_QUADS; ++s) {
             mbar_init(&res_full[s], 1);
             mbar_init(&res_empty[s], 1);
         }
-        for (int s = 0; s < PG_NOUT; ++s) mbar_init(&out_empty[s], 1);
         mbar_init(b_full, 1);
         fence_barrier_init();
     }
@@ -106,32 +130,36 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                 mbar_expect_tx(b_full, (uint32_t)(k_iters * Cfg::B_BYTES));
                 for (int it = 0; it < k_iters; ++it) tma_load_2d(&maps.b, b_full, sB + it * B_BYTES, it * BK, n0);
             }
-            uint32_t na = 0, cq = 0;
+            TileWalk tw;
+            tw.init(m_first, pp.grid_m, p.tiles_x, p.tiles_y);
+            int s = 0, rq = 0;
+            uint32_t ph = 0, rph = 0;
             for (int j = 0; j < my_tiles; ++j) {
-                const int tile = m_first + j * pp.grid_m;
-                const int tx_i = tile % p.tiles_x, ty_i = (tile / p.tiles_x) % p.tiles_y, b = tile / tiles_xy;
-                const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
-                for (int it = 0; it < k_iters; ++it, ++na) {
-                    const int s = na % SA;
-                    mbar_wait(&a_empty[s], ((na / SA) & 1) ^ 1);
-                    const int tap = it / p.cpt, ch = it - tap * p.cpt;
+                const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, b = tw.b;
+                int tap = 0, ch = 0;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&a_empty[s], ph ^ 1);
+                    TL(0, 1);
                     uint8_t* sa = sRing + s * STAGE_BYTES;
                     mbar_expect_tx(&a_full[s], RESIDENT_B ? A_BYTES : A_BYTES + Cfg::B_BYTES);
                     tma_load_5d(&maps.a, &a_full[s], sa, ch * BK, x0 + p.tap_dx[tap], p.tap_dyi[tap], y0 + p.tap_dy[tap], b);
                     if (!RESIDENT_B) tma_load_2d(&maps.b, &a_full[s], sa + A_BYTES, it * BK, n0);
+                    if (++ch == p.cpt) { ch = 0; ++tap; }
+                    if (++s == SA) { s = 0; ph ^= 1; }
                 }
                 if (p.has_res) {
-                    // residual chunks of this tile, prefetched PG_NRES chunks ahead of the epilogue
-                    for (int c = 0; c < NCH; ++c, ++cq) {
-                        const int buf = cq % PG_NRES;
-                        mbar_wait(&res_empty[buf], ((cq / PG_NRES) & 1) ^ 1);
-                        const int n = n0 + c * CW;
-                        const int g = p.out_mode != OUT_NHWC ? n / p.cout : 0;
-                        const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
-                        mbar_expect_tx(&res_full[buf], CH_BYTES);
-                        tma_load_4d(&maps.r[g], &res_full[buf], sRes + buf * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
+                    // residual chunks of this tile, prefetched into the consuming quad's buffer NQ chunks ahead
+                    int n = n0;
+                    for (int c = 0; c < NCH; ++c, n += CW) {
+                        mbar_wait(&res_empty[rq], rph ^ 1);
+                        int g = 0, co = n;
+                        if (p.out_mode != OUT_NHWC) { g = n / p.cout; co = n - g * p.cout; }
+                        mbar_expect_tx(&res_full[rq], CH_BYTES);
+                        tma_load_4d(&maps.r[g], &res_full[rq], sRes + rq * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
+                        if (++rq == NQ) { rq = 0; rph ^= 1; }
                     }
                 }
+                tw.step();
             }
         }
     } else if (warp == 1) {
@@ -141,16 +169,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             mbar_wait(b_full, 0);
             tc_fence_after();
         }
-        uint32_t nm = 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (int j = 0; j < my_tiles; ++j) {
             const int a = j & 1;
-            mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+            mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1);  // every chunk of the tile that used this accumulator is converted
             tc_fence_after();
+            if (lane == 0) TL(1024, 2);
             const uint32_t tacc = tmem_base + (uint32_t)(a * BLOCK_N);
-            for (int it = 0; it < k_iters; ++it, ++nm) {
-                const int s = nm % SA;
-                mbar_wait(&a_full[s], (nm / SA) & 1);
+            for (int it = 0; it < k_iters; ++it) {
+                mbar_wait(&a_full[s], ph);
                 tc_fence_after();
+                if (lane == 0) TL(1024, 3);
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(sRing + s * STAGE_BYTES);
                     const uint32_t sb = RESIDENT_B ? smem_u32(sB + it * B_BYTES) : sa + A_BYTES;
@@ -164,51 +194,59 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                     if (it == k_iters - 1) umma_commit(&acc_full[a]);
                 }
                 __syncwarp();
+                if (++s == SA) { s = 0; ph ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..17) =====================
-        const int lane_grp = warp & 3;
-        const int part = (warp - 2) >> 2;   // which 16-column blocks of a chunk this warp converts
-        const int r = lane_grp * 32 + lane;
-        const bool leader = (warp == 2 && lane == 0);
+        // ===================== epilogue quads (warps 2..17) =====================
+        const int quad = (warp - 2) >> 2;     // 0..3
+        const int lane_grp = warp & 3;        // TMEM lanes [32*lane_grp, +32)
+        const int r = lane_grp * 32 + lane;   // row of the tile == staging row
+        const bool qleader = (((warp - 2) & 3) == 0) && lane == 0;  // first warp of the quad
         const int act = p.act;
         const bool has_res = p.has_res != 0, res_first = p.res_before_act != 0;
-        uint32_t cq = 0, released = 0;
-        for (int j = 0; j < my_tiles; ++j) {
-            const int tile = m_first + j * pp.grid_m;
-            const int tx_i = tile % p.tiles_x, ty_i = (tile / p.tiles_x) % p.tiles_y, b = tile / tiles_xy;
-            const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
-            const int a = j & 1;
-            mbar_wait(&acc_full[a], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N);
-#pragma unroll 1
-            for (int c = 0; c < NCH; ++c, ++cq) {
-                const int buf = cq % NOUT, rbuf = cq % PG_NRES;
-                mbar_wait(&out_empty[buf], ((cq / NOUT) & 1) ^ 1);        // the store issued NOUT chunks ago has read this buffer
-                if (has_res) mbar_wait(&res_full[rbuf], (cq / PG_NRES) & 1);  // residual chunk landed
-                uint8_t* bufp = sOut + buf * CH_BYTES;
-                const uint8_t* resp = sRes + rbuf * CH_BYTES;
-#pragma unroll 1
-                for (int sub = part; sub < CW / 16; sub += PG_EPI_WARPS / 4) {
-                    uint32_t acc[16];
-                    tmem_ld16(trow + c * CW + sub * 16, acc);
-                    tmem_ld_wait();
-                    const uint32_t o0 = stage_off<CW>(r, 2 * sub), o1 = stage_off<CW>(r, 2 * sub + 1);
-                    uint4* s0 = reinterpret_cast<uint4*>(bufp + o0);
-                    uint4* s1 = reinterpret_cast<uint4*>(bufp + o1);
-                    float v[16];
-                    {
-                        const float4* bp = reinterpret_cast<const float4*>(sBias + c * CW + sub * 16);  // smem broadcast
+        if (quad < NQ && my_tiles > 0) {
+            uint8_t* bufp = sOut + quad * CH_BYTES;
+            const uint8_t* resp = sRes + quad * CH_BYTES;
+            const int tlb = quad == 0 ? 2048 : 3072;
+            const bool tlq = qleader && quad < 2;
+            // this quad converts chunks quad, quad+NQ, ... of the CTA's chunk sequence (tile-major, NCH chunks per tile)
+            int j = quad / NCH, c = quad - j * NCH;
+            TileWalk tw;
+            tw.init(m_first, pp.grid_m, p.tiles_x, p.tiles_y);
+            for (int jj = 0; jj < j; ++jj) tw.step();
+            uint32_t rph = 0;
+            bool first = true;
+            while (j < my_tiles) {
+                const int a = j & 1;
+                if (qleader && !first) tma_store_wait_read();   // my previous store has finished reading this quad's buffer
+                first = false;
+                mbar_wait(&acc_full[a], (j >> 1) & 1);
+                if (has_res) mbar_wait(&res_full[quad], rph);
+                tc_fence_after();
+                asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");   // buffer free (leader waited) for all 4 warps
+                if (tlq) TL(tlb, 5);
+                const uint32_t tcol = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N + c * CW);
+                constexpr int PAIR = NSUB >= 2 ? 2 : 1;   // two 16-column TMEM loads in flight per wait
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 bq = bp[q];
-                            v[4 * q] = __uint_as_float(acc[4 * q]) + bq.x;
-                            v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + bq.y;
-                            v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + bq.z;
-                            v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + bq.w;
-                        }
+              for (int sp = 0; sp < NSUB; sp += PAIR) {
+                uint32_t acc[PAIR][16];
+#pragma unroll
+                for (int u = 0; u < PAIR; ++u) tmem_ld16(tcol + (sp + u) * 16, acc[u]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < PAIR; ++u) {
+                    const int sub = sp + u;
+                    const uint32_t o0 = stage_off<CW>(r, 2 * sub), o1 = stage_off<CW>(r, 2 * sub + 1);
+                    float v[16];
+                    const float4* bp = reinterpret_cast<const float4*>(sBias + c * CW + sub * 16);  // smem broadcast
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bq = bp[q];
+                        v[4 * q] = __uint_as_float(acc[u][4 * q]) + bq.x;
+                        v[4 * q + 1] = __uint_as_float(acc[u][4 * q + 1]) + bq.y;
+                        v[4 * q + 2] = __uint_as_float(acc[u][4 * q + 2]) + bq.z;
+                        v[4 * q + 3] = __uint_as_float(acc[u][4 * q + 3]) + bq.w;
                     }
                     if (has_res) {
                         float rv[16];
@@ -235,31 +273,31 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                     __align__(16) __half2 o[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) o[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-                    *s0 = reinterpret_cast<const uint4*>(o)[0];
-                    *s1 = reinterpret_cast<const uint4*>(o)[1];
+                    *reinterpret_cast<uint4*>(bufp + o0) = reinterpret_cast<const uint4*>(o)[0];
+                    *reinterpret_cast<uint4*>(bufp + o1) = reinterpret_cast<const uint4*>(o)[1];
                 }
-                if (c == NCH - 1) tc_fence_before();  // this tile's TMEM reads are done before the barrier below
-                fence_async_smem();
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * PG_EPI_WARPS) : "memory");
-                if (leader) {
-                    if (c == NCH - 1) mbar_arrive(&acc_empty[a]);  // hand the accumulator back to the MMA warp
-                    if (has_res) mbar_arrive(&res_empty[rbuf]);    // residual chunk consumed by every epilogue thread
+              }
+                if (tlq) TL(tlb, 6);
+                tc_fence_before();       // TMEM reads of this chunk are complete
+                fence_async_smem();      // staging writes visible to the TMA (async proxy)
+                asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");
+                if (qleader) {
+                    mbar_arrive(&acc_empty[a]);                    // 1 of NCH arrivals that hand the accumulator back
+                    if (has_res) mbar_arrive(&res_empty[quad]);    // residual chunk consumed
                     const int n = n0 + c * CW;
-                    const int g = p.out_mode != OUT_NHWC ? n / p.cout : 0;
-                    const int co = p.out_mode != OUT_NHWC ? n - g * p.cout : n;
-                    tma_store_4d(&maps.o[g], bufp, co, x0, y0, b);
+                    int g = 0, co = n;
+                    if (p.out_mode != OUT_NHWC) { g = n / p.cout; co = n - g * p.cout; }
+                    // out-of-range rows/cols of edge tiles are clipped by the TMA unit
+                    tma_store_4d(&maps.o[g], bufp, co, tw.tx * p.TW, tw.ty * p.TH, tw.b);
                     tma_store_commit();
-                    // all but the 2 newest stores have read their staging buffers: hand those buffers back.  With 4
-                    // buffers the next chunk's buffer was already handed back one chunk earlier (off the critical path).
-                    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-                    while (released + 2 <= cq) {
-                        mbar_arrive(&out_empty[released % NOUT]);
-                        ++released;
-                    }
+                    if (tlq) TL(tlb, 9);
                 }
+                rph ^= 1;
+                c += NQ;
+                while (c >= NCH) { c -= NCH; ++j; tw.step(); }
             }
+            if (qleader) tma_store_wait_read();
         }
-        if (leader) tma_store_wait_read();
         tc_fence_before();
     }
     __syncthreads();
@@ -267,6 +305,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
         tc_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
     }
+#undef TL
 }
 
 }  // namespace nb200

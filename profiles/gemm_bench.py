@@ -40,7 +40,7 @@ def floor_us(R, Wb):
 
 shapes = [("qkv", 192, 576, 0, False), ("proj", 192, 192, 0, True), ("fc1", 192, 384, 2, False), ("fc2", 384, 192, 0, True),
           ("qkv96", 96, 288, 0, False), ("fc1_96", 96, 192, 2, False), ("toimg", 192, 48, 0, False)]
-variants = [("default", {}), ("nout3", {0: 3}), ("stages3", {1: 3}), ("grid74", {2: 74}), ("grid120", {2: 120})]
+variants = [("default", {}), ("nq3", {0: 3}), ("nq2", {0: 2}), ("grid74", {2: 74})]
 res_all = {}
 for name, K, N, act, use_res in shapes:
     A = torch.randn(T, K, device=dev).half()
