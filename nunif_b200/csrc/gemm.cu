@@ -112,6 +112,8 @@ static int launch_persistent_t(cudaStream_t st, const GemmMaps& maps, const Gemm
     const int grid = grid_m * p.n_tiles;
     constexpr int b_chunk = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
     pp.nq = p.has_res ? 3 : g_tune[0];
+    // the quads' chunks in flight must never span more than the 2 TMEM accumulators (mbarrier phases are 1 bit)
+    if (pp.nq > 2 * Cfg::NCH) pp.nq = 2 * Cfg::NCH;
     pp.timeline = g_timeline;
     const int stg = pp.nq * (p.has_res ? 2 : 1) * Cfg::CH_BYTES + BN * 4 /*bias*/;
     // weights resident in shared memory when they fit next to >= 3 activation stages
