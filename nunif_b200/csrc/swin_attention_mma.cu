@@ -1,6 +1,6 @@
 // Shifted-window attention core on tensor cores (mma.sync m16n8k16, fp16 in / fp32 accumulate).
 //
-// One CTA per 6x6 window, one warp per head (6 warps), 3 CTAs per SM.  q/k/v rows are staged with
+// One CTA per 6x6 window, one warp per head (6 warps), 4 CTAs per SM.  q/k/v rows are staged with
 // cp.async (16-byte LDGSTS, no register round trip).  The 36 tokens are padded to 48 MMA rows by clamping
 // the row index (padded keys are masked by select, padded probabilities are exactly 0):
 //   S = (Q*scale) K^T : M=48 (3 m16 tiles), N=48 (6 n8 tiles), K=d (d/16 steps)
@@ -44,7 +44,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 template <int D>
-__global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
+__global__ void __launch_bounds__(192, 4) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
                                                                    __half* __restrict__ out, int H, int W, int shift,
                                                                    size_t plane) {
     constexpr int C = D * HEADS;
@@ -92,85 +92,64 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
 
     const int head = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int hc = head * D;
-    // ---- S = Q K^T
-    float s[3][6][4];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
+    const float scale = ((D == 16) ? 0.25f : 0.17677669529663687f) * 1.4426950408889634f;  // (C//heads)**-0.5 (:187) * log2(e)
+    const bool boundary = shift > 0 && (wy == gridDim.x / nww - 1 || wx == nww - 1);  // only these windows mix mask regions
+    const float4* bf = bias_frag + (size_t)head * (3 * 6 * 32) + lane;
+    // One 16-row m-tile at a time (rows 0-15, 16-31, 32-47): keeps the live state at 24 + 4*D/8 accumulators so that
+    // 4 CTAs fit per SM; K / V fragments are re-read from shared memory per m-tile (cheap, conflict-free).
+#pragma unroll 1
+    for (int mt = 0; mt < 3; ++mt) {
+        const int row0 = min(mt * 16 + g, WTOK - 1), row1 = min(mt * 16 + g + 8, WTOK - 1);
+        // ---- S = Q K^T
+        float s[6][4];
 #pragma unroll
         for (int nt = 0; nt < 6; ++nt)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) s[mt][nt][r] = 0.f;
+            for (int r = 0; r < 4; ++r) s[nt][r] = 0.f;
 #pragma unroll
-    for (int kt = 0; kt < D / 16; ++kt) {
-        uint32_t a[3][4];
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-            const __half* p0 = sq + min(mt * 16 + g, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
-            const __half* p1 = sq + min(mt * 16 + g + 8, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
-            a[mt][0] = *reinterpret_cast<const uint32_t*>(p0);
-            a[mt][1] = *reinterpret_cast<const uint32_t*>(p1);
-            a[mt][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
-            a[mt][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 6; ++nt) {
-            const __half* pk = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pk);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pk + 8);
-#pragma unroll
-            for (int mt = 0; mt < 3; ++mt) mma16816(s[mt][nt], a[mt], b0, b1);
-        }
-    }
-    // ---- bias + mask + softmax on the fragments.  element r of (mt, nt): row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1)
-    // bias_frag holds log2(e) * relative_position_bias in exactly this fragment order (padded keys = -1e30), so the
-    // whole "scale, add bias, mask padding" step is one FMA per element and the softmax runs in base 2.
-    const float scale = ((D == 16) ? 0.25f : 0.17677669529663687f) * 1.4426950408889634f;  // (C//heads)**-0.5 (:187) * log2(e)
-    {
-        const float4* bf = bias_frag + (size_t)head * (3 * 6 * 32) + lane;
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
+        for (int kt = 0; kt < D / 16; ++kt) {
+            uint32_t a[4];
+            const __half* p0 = sq + row0 * LD + hc + kt * 16 + 2 * t4;
+            const __half* p1 = sq + row1 * LD + hc + kt * 16 + 2 * t4;
+            a[0] = *reinterpret_cast<const uint32_t*>(p0);
+            a[1] = *reinterpret_cast<const uint32_t*>(p1);
+            a[2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+            a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
 #pragma unroll
             for (int nt = 0; nt < 6; ++nt) {
-                const float4 bv = __ldg(bf + (mt * 6 + nt) * 32);
-                s[mt][nt][0] = fmaf(s[mt][nt][0], scale, bv.x);
-                s[mt][nt][1] = fmaf(s[mt][nt][1], scale, bv.y);
-                s[mt][nt][2] = fmaf(s[mt][nt][2], scale, bv.z);
-                s[mt][nt][3] = fmaf(s[mt][nt][3], scale, bv.w);
+                const __half* pk = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
+                mma16816(s[nt], a, *reinterpret_cast<const uint32_t*>(pk), *reinterpret_cast<const uint32_t*>(pk + 8));
             }
-    }
-    if (shift > 0 && (wy == gridDim.x / nww - 1 || wx == nww - 1)) {
-        // only the last window row / column of a shifted map mixes regions (:193-209): -100 across regions
-        int creg[6][2];
+        }
+        // ---- scale + bias (+ mask).  element r of tile nt: row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1).
+        // bias_frag holds log2(e)*relative_position_bias in exactly this fragment order (padded keys = -1e30), so
+        // scale + bias + key padding is one FMA per element and the softmax runs in base 2.
 #pragma unroll
-        for (int nt = 0; nt < 6; ++nt)
+        for (int nt = 0; nt < 6; ++nt) {
+            const float4 bv = __ldg(bf + (mt * 6 + nt) * 32);
+            s[nt][0] = fmaf(s[nt][0], scale, bv.x);
+            s[nt][1] = fmaf(s[nt][1], scale, bv.y);
+            s[nt][2] = fmaf(s[nt][2], scale, bv.z);
+            s[nt][3] = fmaf(s[nt][3], scale, bv.w);
+        }
+        if (boundary) {  // -100 across regions (:193-209)
+            const int q0 = sreg[row0], q1 = sreg[row1];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) creg[nt][e] = sreg[min(nt * 8 + 2 * t4 + e, WTOK - 1)];
+            for (int nt = 0; nt < 6; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-                const int qreg = sreg[min(mt * 16 + g + 8 * hlf, WTOK - 1)];
-#pragma unroll
-                for (int nt = 0; nt < 6; ++nt)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        if (creg[nt][e] != qreg) s[mt][nt][2 * hlf + e] += -100.0f * 1.4426950408889634f;
-            }
-    }
-    float inv_sum[3][2];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt) {
+                for (int e = 0; e < 2; ++e) {
+                    const int cr = sreg[min(nt * 8 + 2 * t4 + e, WTOK - 1)];
+                    if (cr != q0) s[nt][e] += -100.0f * 1.4426950408889634f;
+                    if (cr != q1) s[nt][2 + e] += -100.0f * 1.4426950408889634f;
+                }
+        }
+        // ---- softmax numerators (base 2); the 1/sum factor is applied to the output rows
+        float inv[2];
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
-            if (mt == 2 && hlf == 1) {  // rows 40..47 never exist: keep P = 0 so they cost nothing downstream
-#pragma unroll
-                for (int nt = 0; nt < 6; ++nt) s[mt][nt][2] = s[mt][nt][3] = 0.f;
-                inv_sum[mt][hlf] = 0.f;
-                continue;
-            }
             float mx = -1e30f;
 #pragma unroll
-            for (int nt = 0; nt < 6; ++nt) mx = fmaxf(mx, fmaxf(s[mt][nt][2 * hlf], s[mt][nt][2 * hlf + 1]));
+            for (int nt = 0; nt < 6; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * hlf], s[nt][2 * hlf + 1]));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             float sum = 0.f;
@@ -178,52 +157,45 @@ __global__ void __launch_bounds__(192, 3) window_attention_mma_kernel(const __ha
             for (int nt = 0; nt < 6; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const float pe = exp2f(s[mt][nt][2 * hlf + e] - mx);
-                    s[mt][nt][2 * hlf + e] = pe;
+                    float pe;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s[nt][2 * hlf + e] - mx));
+                    s[nt][2 * hlf + e] = pe;
                     sum += pe;
                 }
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            inv_sum[mt][hlf] = 1.f / sum;
+            inv[hlf] = __fdividef(1.f, sum);
         }
-    }
-    // ---- O = P V
-    float o[3][D / 8][4];
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
+        // ---- O = P V  (P in fp16, un-normalised: values in [0, 1])
+        float o[D / 8][4];
 #pragma unroll
         for (int nt = 0; nt < D / 8; ++nt)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) o[mt][nt][r] = 0.f;
+            for (int r = 0; r < 4; ++r) o[nt][r] = 0.f;
 #pragma unroll
-    for (int kt = 0; kt < 3; ++kt) {
-        uint32_t a[3][4];
+        for (int kt = 0; kt < 3; ++kt) {
+            uint32_t a[4];
+            a[0] = pack_half2(s[2 * kt][0], s[2 * kt][1]);
+            a[1] = pack_half2(s[2 * kt][2], s[2 * kt][3]);
+            a[2] = pack_half2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+            a[3] = pack_half2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-            // normalised probabilities in fp16 (the reference casts the softmax output to fp16 for attn @ v)
-            a[mt][0] = pack_half2(s[mt][2 * kt][0] * inv_sum[mt][0], s[mt][2 * kt][1] * inv_sum[mt][0]);
-            a[mt][1] = pack_half2(s[mt][2 * kt][2] * inv_sum[mt][1], s[mt][2 * kt][3] * inv_sum[mt][1]);
-            a[mt][2] = pack_half2(s[mt][2 * kt + 1][0] * inv_sum[mt][0], s[mt][2 * kt + 1][1] * inv_sum[mt][0]);
-            a[mt][3] = pack_half2(s[mt][2 * kt + 1][2] * inv_sum[mt][1], s[mt][2 * kt + 1][3] * inv_sum[mt][1]);
+            for (int nt = 0; nt < D / 8; ++nt) {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(b0, b1, sv + min(kt * 16 + (lane & 15), WTOK - 1) * LD + hc + nt * 8);
+                mma16816(o[nt], a, b0, b1);
+            }
         }
+        // ---- stage this head's output columns into sq.  Each warp only ever reads and writes its own columns of
+        // rows [16*mt, 16*mt+16) here, and those q rows are dead once this m-tile's S is done.
+        __syncwarp();
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
 #pragma unroll
         for (int nt = 0; nt < D / 8; ++nt) {
-            uint32_t b0, b1;
-            ldmatrix_x2_trans(b0, b1, sv + min(kt * 16 + (lane & 15), WTOK - 1) * LD + hc + nt * 8);
-#pragma unroll
-            for (int mt = 0; mt < 3; ++mt) mma16816(o[mt][nt], a[mt], b0, b1);
+            if (r0 < WTOK) *reinterpret_cast<uint32_t*>(sq + r0 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[nt][0] * inv[0], o[nt][1] * inv[0]);
+            if (r1 < WTOK) *reinterpret_cast<uint32_t*>(sq + r1 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[nt][2] * inv[1], o[nt][3] * inv[1]);
         }
     }
-    // ---- stage the head's output columns into sq (each warp owns its own columns), then coalesced stores
-    __syncwarp();
-#pragma unroll
-    for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < D / 8; ++nt) {
-            const int r0 = mt * 16 + g, r1 = r0 + 8;
-            if (r0 < WTOK) *reinterpret_cast<uint32_t*>(sq + r0 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[mt][nt][0], o[mt][nt][1]);
-            if (r1 < WTOK) *reinterpret_cast<uint32_t*>(sq + r1 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[mt][nt][2], o[mt][nt][3]);
-        }
     __syncthreads();
     for (int t = rg; t < WTOK; t += RG)
         *reinterpret_cast<uint4*>(out + (size_t)stok[t] * C + vv * 8) = *reinterpret_cast<const uint4*>(sq + t * LD + vv * 8);
