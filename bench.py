@@ -258,10 +258,13 @@ def run_b200(args):
     value = world * args.steps * mp / (ms / 1e3)
     e2e = world * e2e_steps * mp / (ms_e2e / 1e3)
     peaks, peak_src = load_peaks()
-    gemm = prof.get("gemm", {"launches": 0, "ms": 0.0, "work": 0.0})
+    gemm = prof.get("gemm", {"launches": 0, "ms": 0.0, "work": 0.0, "hbm_bytes": 0.0, "hbm_floor_ms": 0.0})
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     ach = gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
     total_prof_ms = sum(v["ms"] for v in prof.values())
+    attn = prof.get("window_attention", {"launches": 0, "ms": 0.0, "work": 0.0, "hbm_bytes": 0.0, "hbm_floor_ms": 0.0})
+    gemm_gbs = gemm.get("hbm_bytes", 0.0) / (gemm["ms"] / 1e3) / 1e9 if gemm["ms"] > 0 else 0.0
+    attn_gbs = attn.get("hbm_bytes", 0.0) / (attn["ms"] / 1e3) / 1e9 if attn["ms"] > 0 else 0.0
     line = {
         "metric": "waifu2x_input_megapixels_per_sec", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -278,11 +281,20 @@ def run_b200(args):
                 "steps": e2e_steps, "note": "pinned host input -> tiled_render -> pinned host output (reference default output_device='cpu')"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit GEMM, all shapes of one frame)",
-                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-                     "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
+        "roofline": {"bound": "hbm", "kernel": "gemm_conv_persistent (tcgen05 implicit GEMM; all GEMM launches of one frame)",
+                     "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
+                     "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs (copy)",
+                     "note": "Swin Linears have 96-144 FLOP/B < the 210 FLOP/B ridge: HBM-bound. achieved = algorithmic bytes "
+                             "(activations in + residual + out, weights once) / event time. frac_of_mix_floor uses the measured "
+                             "write-only (3.92 TB/s) and read-only (6.2 TB/s) limits per launch (profiles/r1/hbm_microbench.json)",
+                     "frac_of_mix_floor": gemm["hbm_floor_ms"] / gemm["ms"] if gemm["ms"] else None,
+                     "tensor_tflops": ach, "tensor_peak_tflops": peak_tf, "tensor_frac": ach / peak_tf if peak_tf else None,
                      "launches": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
                      "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None, "traffic": None},
+        "roofline_attention": {"bound": "hbm", "kernel": "window_attention_mma_kernel", "achieved": attn_gbs, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": attn_gbs / peaks["hbm_gbs"],
+                               "frac_of_mix_floor": attn["hbm_floor_ms"] / attn["ms"] if attn["ms"] else None,
+                               "share_of_step": attn["ms"] / total_prof_ms if total_prof_ms else None},
         "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }
     if iw3 is not None:

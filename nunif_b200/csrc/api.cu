@@ -11,7 +11,9 @@ thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_prof_enabled{0};
 
-struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+struct ProfRec { cudaEvent_t a, b; int cat; double work, rb, wb; };
+// measured HBM rates of this pool (profiles/r1/hbm_microbench.json): copy, write-only, read-only, bytes/s
+static double g_bw_copy = 6.6e12, g_bw_write = 3.92e12, g_bw_read = 6.2e12;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
@@ -25,9 +27,9 @@ static cudaEvent_t prof_event() {
     cudaEventCreate(&e);
     return e;
 }
-void prof_begin(cudaStream_t st, int cat, double work) {
+void prof_begin(cudaStream_t st, int cat, double work, double rb, double wb) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    ProfRec r; r.a = prof_event(); r.b = prof_event(); r.cat = cat; r.work = work;
+    ProfRec r; r.a = prof_event(); r.b = prof_event(); r.cat = cat; r.work = work; r.rb = rb; r.wb = wb;
     cudaEventRecord(r.a, st);
     g_prof_recs.push_back(r);
 }
@@ -71,19 +73,27 @@ extern "C" int nb200_profile_report(char* buf, size_t cap) {
     NB_CHECK(buf && cap > 0, "null buffer");
     NB_CUDA(cudaDeviceSynchronize());
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    double ms[PC_COUNT] = {0}, work[PC_COUNT] = {0};
+    double ms[PC_COUNT] = {0}, work[PC_COUNT] = {0}, floor_ms[PC_COUNT] = {0}, bytes[PC_COUNT] = {0};
     long n[PC_COUNT] = {0};
     for (auto& r : g_prof_recs) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cat] += t; work[r.cat] += r.work; n[r.cat]++; }
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            ms[r.cat] += t; work[r.cat] += r.work; n[r.cat]++;
+            // per-launch traffic-mix HBM floor: max((R+W)/copy, W/write_only, R/read_only)
+            double f = (r.rb + r.wb) / g_bw_copy;
+            if (r.wb / g_bw_write > f) f = r.wb / g_bw_write;
+            if (r.rb / g_bw_read > f) f = r.rb / g_bw_read;
+            floor_ms[r.cat] += f * 1e3;
+            bytes[r.cat] += r.rb + r.wb;
+        }
     }
     std::string s = "{";
     bool first = true;
     for (int c = 0; c < PC_COUNT; ++c) {
         if (!n[c]) continue;
         char tmp[256];
-        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kCatNames[c], n[c],
-                 ms[c], work[c]);
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"work\": %.6e, \"hbm_bytes\": %.6e, \"hbm_floor_ms\": %.6f}",
+                 first ? "" : ", ", kCatNames[c], n[c], ms[c], work[c], bytes[c], floor_ms[c]);
         s += tmp;
         first = false;
     }

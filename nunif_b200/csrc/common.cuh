@@ -42,13 +42,15 @@ inline int fail(const std::string& msg) {
 enum ProfCat : int { PC_GEMM = 0, PC_ATTN, PC_STEM, PC_TOIMG, PC_UNFOLD, PC_BLEND, PC_SE, PC_TAIL, PC_WARP_FW, PC_WARP_BW,
                      PC_DILATE, PC_MINMAX, PC_OTHER, PC_COUNT };
 extern std::atomic<int> g_prof_enabled;
-void prof_begin(cudaStream_t st, int cat, double work);
+void prof_begin(cudaStream_t st, int cat, double work, double rbytes, double wbytes);
 void prof_end(cudaStream_t st);
 struct ProfScope {
     cudaStream_t st;
     bool on;
-    ProfScope(cudaStream_t s, int cat, double work) : st(s), on(g_prof_enabled.load(std::memory_order_relaxed) != 0) {
-        if (on) prof_begin(st, cat, work);
+    // work = FLOPs (tensor-bound classes) or algorithmic bytes; rbytes/wbytes = algorithmic HBM reads/writes (0 = unknown)
+    ProfScope(cudaStream_t s, int cat, double work, double rbytes = 0, double wbytes = 0)
+        : st(s), on(g_prof_enabled.load(std::memory_order_relaxed) != 0) {
+        if (on) prof_begin(st, cat, work, rbytes, wbytes);
     }
     ~ProfScope() {
         if (on) prof_end(st);

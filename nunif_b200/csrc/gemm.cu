@@ -284,7 +284,12 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         p.res_cx = p.res_cy = 0;
     }
     const int m_tiles = p.tiles_x * p.tiles_y * p.B;
-    ProfScope ps(st, PC_GEMM, 2.0 * (double)p.B * p.Ho * p.Wo * (double)g.N * (double)K);
+    const double Mrows = (double)p.B * p.Ho * p.Wo;
+    // algorithmic HBM traffic: the input region once (taps re-read from L2), the residual, the output
+    const double in_px = g.kind == CG_DOWN2 ? 4.0 * Mrows : (g.kind == CG_CONV3 ? (double)p.B * g.Hi * g.Wi : Mrows);
+    ProfScope ps(st, PC_GEMM, 2.0 * Mrows * (double)g.N * (double)K,
+                 in_px * (g.kind == CG_LINEAR_FLAT ? g.Cin * g.a_planes : g.Cin) * 2.0 + (g.res ? Mrows * g.N * 2.0 : 0.0) + (double)g.N * K * 2.0,
+                 Mrows * (double)g.N * 2.0);
     static const bool legacy = getenv("NB200_GEMM_NONPERSISTENT") != nullptr;  // A/B switch for profiling only
     if (legacy) return BK == 64 ? launch_bn<64>(bn, st, maps, p, m_tiles, p.n_tiles) : launch_bn<32>(bn, st, maps, p, m_tiles, p.n_tiles);
     return BK == 64 ? launch_persistent_bn<64>(bn, st, maps, p, m_tiles) : launch_persistent_bn<32>(bn, st, maps, p, m_tiles);

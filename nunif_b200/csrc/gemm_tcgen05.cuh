@@ -173,7 +173,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
     q = fmaf(q, a, 5.21468017e-02f);
     q = fmaf(q, a, 4.59595724e-01f);
     q = fmaf(q, a, 1.15100057e+00f);
-    const float e = 0.5f * exp2f(-q * a);      // Phi(-|x|)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q * a));   // erfc(|x|/sqrt2): one MUFU.EX2, no range fix-up code
+    e *= 0.5f;                                                     // Phi(-|x|)
     return x * (x > 0.f ? 1.0f - e : e);
 }
 

@@ -95,6 +95,13 @@ __global__ void __launch_bounds__(192, 4) window_attention_mma_kernel(const __ha
     const float scale = ((D == 16) ? 0.25f : 0.17677669529663687f) * 1.4426950408889634f;  // (C//heads)**-0.5 (:187) * log2(e)
     const bool boundary = shift > 0 && (wy == gridDim.x / nww - 1 || wx == nww - 1);  // only these windows mix mask regions
     const float4* bf = bias_frag + (size_t)head * (3 * 6 * 32) + lane;
+    // per-thread fragment base pointers (row clamps and column offsets resolved once)
+    const __half* kbase[6];
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) kbase[nt] = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + 2 * t4;
+    const __half* vbase[3];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) vbase[kt] = sv + min(kt * 16 + (lane & 15), WTOK - 1) * LD + hc;
     // One 16-row m-tile at a time (rows 0-15, 16-31, 32-47): keeps the live state at 24 + 4*D/8 accumulators so that
     // 4 CTAs fit per SM; K / V fragments are re-read from shared memory per m-tile (cheap, conflict-free).
 #pragma unroll 1
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(192, 4) window_attention_mma_kernel(const __ha
             a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
 #pragma unroll
             for (int nt = 0; nt < 6; ++nt) {
-                const __half* pk = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + kt * 16 + 2 * t4;
+                const __half* pk = kbase[nt] + kt * 16;
                 mma16816(s[nt], a, *reinterpret_cast<const uint32_t*>(pk), *reinterpret_cast<const uint32_t*>(pk + 8));
             }
         }
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(192, 4) window_attention_mma_kernel(const __ha
 #pragma unroll
             for (int nt = 0; nt < D / 8; ++nt) {
                 uint32_t b0, b1;
-                ldmatrix_x2_trans(b0, b1, sv + min(kt * 16 + (lane & 15), WTOK - 1) * LD + hc + nt * 8);
+                ldmatrix_x2_trans(b0, b1, vbase[kt] + nt * 8);
                 mma16816(o[nt], a, b0, b1);
             }
         }
@@ -242,7 +249,7 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_
     NB_CHECK(C == 96 || C == 192, "window attention supports C=96 (d=16) and C=192 (d=32)");
     if (WS >= H) shift = 0;  // torchvision :151-155
     dim3 grid((H / WS) * (W / WS), B);
-    ProfScope ps(st, PC_ATTN, (double)B * H * W * C * 4 * 2);  // bytes: read q,k,v + write out
+    ProfScope ps(st, PC_ATTN, (double)B * H * W * C * 4 * 2, (double)B * H * W * C * 3 * 2, (double)B * H * W * C * 2);  // q,k,v in; out
     if (C == 96) {
         static bool cfg = false;
         if (!cfg) {
