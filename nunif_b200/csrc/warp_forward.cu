@@ -1,4 +1,4 @@
-// Depth-ordered bilinear forward warp (splat) + hole handling, one CTA per image row.
+// Depth-ordered bilinear forward warp (splat) + hole handling, one CTA per (image row, eye).
 //
 // Replaces iw3/forward_warp.py:140-243 (depth_order_bilinear_forward_warp):
 //   global argsort of B*H*W depths + 4 deterministic index_copy_ scatters + iterative
@@ -27,7 +27,7 @@
 
 namespace nb200 {
 
-constexpr int FW_THREADS = 256;
+constexpr int FW_THREADS = 512;
 constexpr int FW_MAX_TRIES = 100;  // forward_warp.py:18,45
 
 struct FwParams {
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(FW_THREADS) forward_warp_row_kernel(FwParams p
     int* SC = SF + Wp;                                            // ceil  winner   -> b
     float* SCR = reinterpret_cast<float*>(SC + Wp);               // scratch (windowed min)
     const int y = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (blockIdx.z == 0 ? !p.do_left : !p.do_right) return;
     const size_t plane = (size_t)p.H * W;
     const float* __restrict__ crow = p.c + ((size_t)b * 3 * p.H + y) * W;
     const bool same = (p.h == p.H) && (p.w == W);
@@ -122,8 +123,9 @@ __global__ void __launch_bounds__(FW_THREADS) forward_warp_row_kernel(FwParams p
         __syncthreads();
     }
 
-    for (int eye = 0; eye < 2; ++eye) {
-        if (eye == 0 ? !p.do_left : !p.do_right) continue;
+    {
+        // one CTA per (row, image, eye): 2x the CTAs and half the serial passes per CTA
+        const int eye = blockIdx.z;
         const float sg = eye == 0 ? 1.f : -1.f;  // left: +index_shift, right: -index_shift (:176-177)
 
         for (int xp = tid; xp < Wp; xp += FW_THREADS) {
@@ -335,7 +337,7 @@ extern "C" int nb200_forward_warp(const float* c, const float* depth, int B, int
     NB_CUDA(cudaFuncSetAttribute(forward_warp_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps(st, PC_WARP_FW, (double)B * H * W * 4 * 9 + (double)B * h * w * 4);
-        forward_warp_row_kernel<<<dim3(H, B), FW_THREADS, smem, st>>>(p);
+        forward_warp_row_kernel<<<dim3(H, B, 2), FW_THREADS, smem, st>>>(p);
     }
     NB_LAUNCHED();
     if (synthetic_view != NB200_VIEW_BOTH) {
