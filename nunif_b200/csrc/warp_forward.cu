@@ -1,4 +1,4 @@
-// Depth-ordered bilinear forward warp (splat) + hole handling, one CTA per (image row, eye).
+// Depth-ordered bilinear forward warp (splat) + hole handling, one CTA per image row.
 //
 // Replaces iw3/forward_warp.py:140-243 (depth_order_bilinear_forward_warp):
 //   global argsort of B*H*W depths + 4 deterministic index_copy_ scatters + iterative
@@ -27,7 +27,7 @@
 
 namespace nb200 {
 
-constexpr int FW_THREADS = 512;
+constexpr int FW_THREADS = 256;
 constexpr int FW_MAX_TRIES = 100;  // forward_warp.py:18,45
 
 struct FwParams {
@@ -42,6 +42,7 @@ struct FwParams {
     float conv_term;   // shift_size*convergence
     int fill, do_left, do_right, compose;
     float scale_y, scale_x;  // AA resize scales (h-1)/(H-1), (w-1)/(W-1)
+    const float4* coltab;    // per output column: {xmin (as int bits), w0, w1, w2} of the AA resize (upsampling only), or null
 };
 
 __device__ __forceinline__ unsigned depth_key(float d) {
@@ -82,6 +83,38 @@ __device__ float aa_bilinear_sample(const float* __restrict__ src, int h, int w,
     return acc;
 }
 
+// Horizontal taps of the AA resize depend only on the output column: computed once per call (upsampling: <= 3 taps).
+__global__ void depth_coltab_kernel(float4* __restrict__ tab, int W, int w, float scale_x) {
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    if (X >= W) return;
+    const float cx = scale_x * ((float)X + 0.5f);
+    const int xmin = max((int)(cx - 1.0f + 0.5f), 0);
+    const int xsize = min((int)(cx + 1.0f + 0.5f), w) - xmin;
+    float wv[3] = {0.f, 0.f, 0.f}, tx = 0.f;
+    for (int j = 0; j < xsize && j < 3; ++j) { wv[j] = tri((float)(j + xmin) - cx + 0.5f); tx += wv[j]; }
+    tab[X] = make_float4(__int_as_float(xmin), wv[0] / tx, wv[1] / tx, wv[2] / tx);
+}
+
+// same arithmetic as aa_bilinear_sample for the upsampling case, with the horizontal taps taken from the table
+__device__ __forceinline__ float aa_bilinear_sample_tab(const float* __restrict__ src, int h, int w, float scale_y, int y,
+                                                        const float4 ct) {
+    const float cy = scale_y * ((float)y + 0.5f);
+    const int ymin = max((int)(cy - 1.0f + 0.5f), 0);
+    const int ysize = min((int)(cy + 1.0f + 0.5f), h) - ymin;
+    const int xmin = __float_as_int(ct.x);
+    float ty = 0.f;
+    for (int i = 0; i < ysize; ++i) ty += tri((float)(i + ymin) - cy + 0.5f);
+    float acc = 0.f;
+    for (int i = 0; i < ysize; ++i) {
+        const float* row = src + (size_t)(ymin + i) * w + xmin;
+        float hs = __ldg(row) * ct.y;
+        if (xmin + 1 < w) hs += __ldg(row + 1) * ct.z;
+        if (xmin + 2 < w) hs += __ldg(row + 2) * ct.w;
+        acc += hs * (tri((float)(i + ymin) - cy + 0.5f) / ty);
+    }
+    return acc;
+}
+
 // Full-resolution depth via the AA resize (used when the caller wants the resized
 // depth materialised, e.g. tests of the resize alone).
 __global__ void depth_resize_aa_kernel(const float* __restrict__ depth, float* __restrict__ out, int B, int H, int W,
@@ -104,7 +137,6 @@ __global__ void __launch_bounds__(FW_THREADS) forward_warp_row_kernel(FwParams p
     int* SC = SF + Wp;                                            // ceil  winner   -> b
     float* SCR = reinterpret_cast<float*>(SC + Wp);               // scratch (windowed min)
     const int y = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    if (blockIdx.z == 0 ? !p.do_left : !p.do_right) return;
     const size_t plane = (size_t)p.H * W;
     const float* __restrict__ crow = p.c + ((size_t)b * 3 * p.H + y) * W;
     const bool same = (p.h == p.H) && (p.w == W);
@@ -114,7 +146,9 @@ __global__ void __launch_bounds__(FW_THREADS) forward_warp_row_kernel(FwParams p
     {
         const float* dsrc = p.depth + (size_t)b * p.h * p.w;
         for (int X = tid; X < W; X += FW_THREADS)
-            DEP[X + P] = same ? dsrc[(size_t)y * W + X] : aa_bilinear_sample(dsrc, p.h, p.w, p.scale_y, p.scale_x, y, X);
+            DEP[X + P] = same ? dsrc[(size_t)y * W + X]
+                              : (p.coltab ? aa_bilinear_sample_tab(dsrc, p.h, p.w, p.scale_y, y, __ldg(p.coltab + X))
+                                          : aa_bilinear_sample(dsrc, p.h, p.w, p.scale_y, p.scale_x, y, X));
         __syncthreads();
         for (int t = tid; t < P; t += FW_THREADS) {
             DEP[t] = DEP[P];
@@ -123,9 +157,8 @@ __global__ void __launch_bounds__(FW_THREADS) forward_warp_row_kernel(FwParams p
         __syncthreads();
     }
 
-    {
-        // one CTA per (row, image, eye): 2x the CTAs and half the serial passes per CTA
-        const int eye = blockIdx.z;
+    for (int eye = 0; eye < 2; ++eye) {
+        if (eye == 0 ? !p.do_left : !p.do_right) continue;
         const float sg = eye == 0 ? 1.f : -1.f;  // left: +index_shift, right: -index_shift (:176-177)
 
         for (int xp = tid; xp < Wp; xp += FW_THREADS) {
@@ -301,15 +334,15 @@ __global__ void copy_eye_kernel(const float* __restrict__ c, float* __restrict__
 using namespace nb200;
 
 extern "C" size_t nb200_forward_warp_workspace(int B, int H, int W, int h, int w) {
-    (void)B; (void)H; (void)W; (void)h; (void)w;
-    return 0;  // the depth resize is fused into the row kernel
+    (void)B;
+    // the depth resize is fused into the row kernel; when it upsamples, the per-column taps live in a small table
+    return (h != H || w != W) ? (size_t)W * sizeof(float4) : 0;
 }
 
 extern "C" int nb200_forward_warp(const float* c, const float* depth, int B, int H, int W, int h, int w,
                                   double divergence, double convergence, int fill, int synthetic_view,
                                   int width_base, int compose, float* left, float* right,
                                   float* left_mask, float* right_mask, void* workspace, void* stream) {
-    (void)workspace;
     NB_CHECK(c && depth && left, "null pointer");
     NB_CHECK(compose == NB200_COMPOSE_NONE || compose == NB200_COMPOSE_SBS, "compose must be NONE or SBS");
     NB_CHECK(compose == NB200_COMPOSE_SBS || right, "right output required");
@@ -331,13 +364,20 @@ extern "C" int nb200_forward_warp(const float* c, const float* depth, int B, int
     p.compose = compose;
     p.scale_y = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
     p.scale_x = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    p.coltab = nullptr;
+    cudaStream_t st0 = (cudaStream_t)stream;
+    if ((h != H || w != W) && workspace && p.scale_x < 1.f && p.scale_y < 1.f) {
+        p.coltab = reinterpret_cast<const float4*>(workspace);
+        depth_coltab_kernel<<<cdiv(W, 256), 256, 0, st0>>>(reinterpret_cast<float4*>(workspace), W, w, p.scale_x);
+        NB_LAUNCHED();
+    }
     const size_t smem = (size_t)p.Wp * 7 * sizeof(float);
     NB_CHECK(smem <= 227 * 1024, "row (with divergence padding) does not fit shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     NB_CUDA(cudaFuncSetAttribute(forward_warp_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps(st, PC_WARP_FW, (double)B * H * W * 4 * 9 + (double)B * h * w * 4);
-        forward_warp_row_kernel<<<dim3(H, B, 2), FW_THREADS, smem, st>>>(p);
+        forward_warp_row_kernel<<<dim3(H, B), FW_THREADS, smem, st>>>(p);
     }
     NB_LAUNCHED();
     if (synthetic_view != NB200_VIEW_BOTH) {

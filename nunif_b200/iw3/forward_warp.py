@@ -31,12 +31,14 @@ def apply_divergence_forward_warp(c, depth, divergence, convergence, method=None
     if return_mask:
         lm = torch.zeros((B, 1, H, W), device=dev, dtype=torch.float32)
         rm = torch.zeros((B, 1, H, W), device=dev, dtype=torch.float32)
+    ws_bytes = _lib.lib().nb200_forward_warp_workspace(B, H, W, h, w)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().nb200_forward_warp(
             _lib.ptr(c), _lib.ptr(depth), B, H, W, h, w, float(divergence), float(convergence), fill,
             VIEWS[synthetic_view], 1 if width_base else 0, compose, _lib.ptr(left), _lib.ptr(right),
             _lib.ptr(lm if synthetic_view != "right" else None), _lib.ptr(rm if synthetic_view != "left" else None),
-            None, _lib.stream_ptr(dev)))
+            _lib.ptr(ws), _lib.stream_ptr(dev)))
     if compose != COMPOSE_NONE:
         return left
     if return_mask:
