@@ -108,6 +108,16 @@ int nb200_model_forward(nb200_model* m, const void* x_nhwc_f16, int n, int tile_
 int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, int W, int tile_size,
                        int batch_size, int downscale, float* out, void* stream);
 
+/* The same render with HOST buffers (planar fp32, pinned for full overlap): one H2D copy of the
+ * frame, then the output is blended and copied back in bands of finished tile rows on a side
+ * stream while later tile batches compute.  `stream` completes after the last band has landed
+ * in out_host.  This is the entry point a non-torch binding uses and the one
+ * bench.py's e2e figure times.  Replaces the host<->device hops around
+ * Waifu2x.render (waifu2x/utils.py:218-243; SeamBlending.tiled_render moves each minibatch with .to(device),
+ * seam_blending.py:94). */
+int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, int W, int tile_size,
+                            int batch_size, int downscale, float* out_host, void* stream);
+
 /* ------------------------------------------------------------------ *
  * Path B: iw3 depth post-processing and stereo warps
  * ------------------------------------------------------------------ */

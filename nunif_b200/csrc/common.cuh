@@ -7,6 +7,8 @@
 #include <string>
 #include <atomic>
 
+struct nb200_tile_config;  // include/nunif_b200.h
+
 namespace nb200 {
 
 extern thread_local std::string g_last_error;
@@ -56,6 +58,10 @@ struct ProfScope {
         if (on) prof_end(st);
     }
 };
+
+// seam_blend.cu: rows [y0, y1) of the blended output (used by the band-pipelined host render in model.cu)
+int tile_gather_blend_rows(const void* z_all, int C, const ::nb200_tile_config* cfg, int scale, int offset, int tile_size,
+                           int blend_size, float* out, int y0, int y1, void* stream);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

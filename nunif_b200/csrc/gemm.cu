@@ -83,7 +83,8 @@ constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*bar
 
 // tuning knobs for profiles/gemm_bench.py (nb200_tune_set); defaults are the shipped configuration
 unsigned long long* g_timeline = nullptr;
-int g_tune[8] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, 0, 0, 0, 0, 0};
+int g_tune[8] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, /*3 force gather backward warp*/ 0,
+                 /*4 forced BLOCK_N*/ 0, /*5 disable GELU->128 rule*/ 0, 0, 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {
@@ -112,8 +113,8 @@ static int launch_persistent_t(cudaStream_t st, const GemmMaps& maps, const Gemm
     const int grid = grid_m * p.n_tiles;
     constexpr int b_chunk = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
     pp.nq = p.has_res ? 3 : g_tune[0];
-    // the quads' chunks in flight must never span more than the 2 TMEM accumulators (mbarrier phases are 1 bit)
-    if (pp.nq > 2 * Cfg::NCH) pp.nq = 2 * Cfg::NCH;
+    // the quads' chunks in flight must never span more than the TMEM accumulator ring (mbarrier phases are 1 bit)
+    if (pp.nq > PgAcc<BN>::NACC * Cfg::NCH) pp.nq = PgAcc<BN>::NACC * Cfg::NCH;
     pp.timeline = g_timeline;
     const int stg = pp.nq * (p.has_res ? 2 : 1) * Cfg::CH_BYTES + BN * 4 /*bias*/;
     // weights resident in shared memory when they fit next to >= 3 activation stages
@@ -239,6 +240,13 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         for (int c : cands) {
             const int w = (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : 16);
             if (g.N % c == 0 && (!shuf || g.cout % w == 0) && (!split || g.cout % c == 0)) { bn = c; cw = w; break; }
+        }
+        // epilogue-heavy launches (GELU): narrower tiles give a 4-deep TMEM accumulator ring, so the quads
+        // rarely wait for the MMA (profiles/r1/timeline_fc1_*.txt); chunks never straddle a split plane (cout % 64 == 0)
+        const int forced = g_tune[4] > 0 ? g_tune[4] : ((g.act == ACT_GELU && g_tune[5] == 0) ? 128 : 0);
+        if (forced > 0 && g.N % forced == 0 && !shuf) {
+            const int w = (forced % 64 == 0) ? 64 : ((forced % 32 == 0) ? 32 : 16);
+            if (!split || g.cout % w == 0) { bn = forced; cw = w; }
         }
     }
     NB_CHECK(bn > 0, "no BLOCK_N divides N");

@@ -59,6 +59,12 @@ struct TileWalk {
     }
 };
 
+template <int BLOCK_N>
+struct PgAcc {
+    static constexpr int NACC = (4 * BLOCK_N <= 512) ? 4 : 2;
+    static constexpr int SHIFT = NACC == 4 ? 2 : 1;
+};
+
 template <int BLOCK_N, int BK, bool RESIDENT_B>
 __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __grid_constant__ GemmMaps maps,
                                                                       const __grid_constant__ PersistParams pp) {
@@ -66,7 +72,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
     constexpr int CW = Cfg::CW, NCH = Cfg::NCH, CH_BYTES = Cfg::CH_BYTES, NSUB = CW / 16;
     constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = ((Cfg::B_BYTES + 1023) / 1024) * 1024;
     constexpr int STAGE_BYTES = RESIDENT_B ? A_BYTES : A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    // accumulator ring in TMEM: 4 tiles deep when they fit in the 512 columns (BLOCK_N <= 128), else 2
+    constexpr int NACC = PgAcc<BLOCK_N>::NACC, ACC_SH = PgAcc<BLOCK_N>::SHIFT;
+    constexpr int TMEM_COLS = NACC * BLOCK_N <= 32 ? 32 : (NACC * BLOCK_N <= 64 ? 64 : (NACC * BLOCK_N <= 128 ? 128 : (NACC * BLOCK_N <= 256 ? 256 : 512)));
     const GemmParams& p = pp.g;
     const int SA = pp.stages, k_iters = pp.k_iters, NQ = pp.nq;
 
@@ -81,8 +89,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + PG_MAX_STAGES;
     uint64_t* acc_full = a_empty + PG_MAX_STAGES;
-    uint64_t* acc_empty = acc_full + 2;
-    uint64_t* res_full = acc_empty + 2;
+    uint64_t* acc_empty = acc_full + 4;
+    uint64_t* res_full = acc_empty + 4;
     uint64_t* res_empty = res_full + PG_MAX_QUADS;
     uint64_t* b_full = res_empty + PG_MAX_QUADS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NACC; ++s) {
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], NCH);   // one arrival per chunk of the tile (from the quad that converted it)
         }
@@ -172,8 +180,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
         int s = 0;
         uint32_t ph = 0;
         for (int j = 0; j < my_tiles; ++j) {
-            const int a = j & 1;
-            mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1);  // every chunk of the tile that used this accumulator is converted
+            const int a = j & (NACC - 1);
+            mbar_wait(&acc_empty[a], ((j >> ACC_SH) & 1) ^ 1);  // every chunk of the tile that used this accumulator is converted
             tc_fence_after();
             if (lane == 0) TL(1024, 2);
             const uint32_t tacc = tmem_base + (uint32_t)(a * BLOCK_N);
@@ -218,10 +226,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             uint32_t rph = 0;
             bool first = true;
             while (j < my_tiles) {
-                const int a = j & 1;
+                const int a = j & (NACC - 1);
                 if (qleader && !first) tma_store_wait_read();   // my previous store has finished reading this quad's buffer
                 first = false;
-                mbar_wait(&acc_full[a], (j >> 1) & 1);
+                mbar_wait(&acc_full[a], (j >> ACC_SH) & 1);
                 if (has_res) mbar_wait(&res_full[quad], rph);
                 tc_fence_after();
                 asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");   // buffer free (leader waited) for all 4 warps

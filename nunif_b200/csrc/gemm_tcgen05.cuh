@@ -174,9 +174,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
     q = fmaf(q, a, 4.59595724e-01f);
     q = fmaf(q, a, 1.15100057e+00f);
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q * a));   // erfc(|x|/sqrt2): one MUFU.EX2, no range fix-up code
-    e *= 0.5f;                                                     // Phi(-|x|)
-    return x * (x > 0.f ? 1.0f - e : e);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(-q, a, -1.0f)));   // Phi(-|x|) = erfc(|x|/sqrt2)/2: one MUFU.EX2
+    // x*Phi(x) = max(x, 0) - |x|*Phi(-|x|) on both sides of zero: no select, 9 instructions per value
+    return fmaxf(x, 0.f) - a * e;
 }
 
 // activation over a 16-value fragment; `act` is warp-uniform, so the switch is hoisted out of the element loop

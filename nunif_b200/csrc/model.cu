@@ -192,6 +192,7 @@ struct nb200_model {
     std::shared_ptr<CUNetW> cu;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
+    cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
     template <typename T>
     T* at(size_t off) const { return reinterpret_cast<T*>(blob + off); }
     int ensure_ws(size_t bytes) {
@@ -420,6 +421,15 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
+    {
+        // frame-level scratch comes from cudaMallocAsync every render: keep freed blocks cached in the device pool
+        // instead of returning them to the driver at each synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     Packer pk;
     for (int i = 0; i < n_tensors; ++i) pk.src[names[i]] = HostTensor{data[i], numel[i], false};
     auto m = new nb200_model();
@@ -455,6 +465,7 @@ extern "C" void nb200_model_destroy(nb200_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->ws) cudaFree(m->ws);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
 }
 
@@ -518,6 +529,70 @@ extern "C" int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, 
         if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile, stream);
     }
     if (!rc) rc = nb200_tile_gather_blend(zall, C, &cfg, scale, offset, tile_size, blend, out, stream);
+    cudaFreeAsync(xb, st);
+    cudaFreeAsync(zall, st);
+    return rc;
+}
+
+// Same render with HOST buffers (the call a non-torch binding makes, and bench.py's e2e leg): the input is copied in once,
+// and the output is blended and copied out in bands - as soon as every tile row covering a band of output rows has been
+// computed, that band is blended on the compute stream and its D2H copy runs on a side stream under the remaining tile
+// batches.  Only the last band's copy is exposed.  Pinned host buffers give the overlap; pageable ones still work.
+extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, int W, int tile_size, int batch_size,
+                                       int downscale, float* out_host, void* stream) {
+    NB_CHECK(m && x_host && out_host, "null pointer");
+    NB_CHECK(C == 3, "models take 3-channel input");
+    NB_CHECK(batch_size > 0, "batch_size must be positive");
+    int scale, offset, blend, S;
+    if (model_out_geometry(m, tile_size, downscale, &scale, &offset, &blend, &S)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    nb200_tile_config cfg;
+    if (nb200_tile_config_create(H, W, scale, offset, tile_size, blend, &cfg)) return 1;
+    if (!m->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = m->copy_stream;
+    const int ntiles = cfg.h_blocks * cfg.w_blocks;
+    __half *xb = nullptr, *zall = nullptr;
+    float *xd = nullptr, *od = nullptr;
+    const size_t xb_elems = (size_t)batch_size * tile_size * tile_size * 8, z_tile = (size_t)3 * S * S;
+    const size_t oplane = (size_t)cfg.y_h * cfg.y_w;
+    NB_CUDA(cudaMallocAsync((void**)&xd, (size_t)C * H * W * 4, st));
+    NB_CUDA(cudaMallocAsync((void**)&od, (size_t)C * oplane * 4, st));
+    NB_CUDA(cudaMallocAsync((void**)&xb, xb_elems * 2, st));
+    NB_CUDA(cudaMallocAsync((void**)&zall, (size_t)ntiles * z_tile * 2, st));
+    NB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)C * H * W * 4, cudaMemcpyHostToDevice, st));
+    int rc = 0, rows_done = 0;
+    for (int t0 = 0; t0 < ntiles && !rc; t0 += batch_size) {
+        const int nb = ntiles - t0 < batch_size ? ntiles - t0 : batch_size;
+        rc = nb200_tile_unfold(xd, C, H, W, &cfg, tile_size, t0, nb, xb, 8, stream);
+        if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile, stream);
+        if (rc) break;
+        // output rows below the first unfinished tile row are final
+        const int rows_full = (t0 + nb) / cfg.w_blocks;
+        int y1 = rows_full >= cfg.h_blocks ? cfg.y_h : rows_full * cfg.output_tile_step;
+        if (y1 > cfg.y_h) y1 = cfg.y_h;
+        if (y1 > rows_done) {
+            rc = tile_gather_blend_rows(zall, C, &cfg, scale, offset, tile_size, blend, od, rows_done, y1, stream);
+            if (rc) break;
+            cudaEvent_t ev;
+            NB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            NB_CUDA(cudaEventRecord(ev, st));
+            NB_CUDA(cudaStreamWaitEvent(cs, ev, 0));
+            NB_CUDA(cudaEventDestroy(ev));   // released once the wait has been satisfied
+            for (int c = 0; c < C; ++c) {
+                const size_t o = (size_t)c * oplane + (size_t)rows_done * cfg.y_w;
+                NB_CUDA(cudaMemcpyAsync(out_host + o, od + o, (size_t)(y1 - rows_done) * cfg.y_w * 4, cudaMemcpyDeviceToHost, cs));
+            }
+            rows_done = y1;
+        }
+    }
+    // the caller's stream completes only after the last band has landed in host memory
+    cudaEvent_t ev_end;
+    NB_CUDA(cudaEventCreateWithFlags(&ev_end, cudaEventDisableTiming));
+    NB_CUDA(cudaEventRecord(ev_end, cs));
+    NB_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+    NB_CUDA(cudaEventDestroy(ev_end));
+    cudaFreeAsync(xd, st);
+    cudaFreeAsync(od, st);
     cudaFreeAsync(xb, st);
     cudaFreeAsync(zall, st);
     return rc;

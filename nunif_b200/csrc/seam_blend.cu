@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) tile_unfold_kernel(const float* __restric
 struct BlendParams {
     const __half* z;
     float* out;
-    int C, S, y_h, y_w, h_blocks, w_blocks, step_out, blend;
+    int C, S, y_h, y_w, h_blocks, w_blocks, step_out, blend, y0;
     float ring[65];  // ring[d] = weight at distance d from the tile edge, d < blend
 };
 
@@ -54,7 +54,7 @@ __device__ __forceinline__ float blend_weight(const BlendParams& p, int u, int v
 
 __global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
     const int X = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Y = blockIdx.y;
+    const int Y = blockIdx.y + p.y0;
     if (X >= p.y_w) return;
     // tiles covering Y: hi with hi*step <= Y < hi*step + S
     const int hi1 = min(Y / p.step_out, p.h_blocks - 1);
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
 // group never straddles a tile edge): 8-byte fp16 loads, one float4 store per colour plane.
 __global__ void __launch_bounds__(256) tile_gather_blend4_kernel(BlendParams p) {
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int Y = blockIdx.y;
+    const int Y = blockIdx.y + p.y0;
     if (X >= p.y_w) return;
     const int hi1 = min(Y / p.step_out, p.h_blocks - 1);
     const int wi1 = min(X / p.step_out, p.w_blocks - 1);
@@ -171,7 +171,15 @@ extern "C" int nb200_tile_unfold(const float* x, int C, int H, int W, const nb20
 
 extern "C" int nb200_tile_gather_blend(const void* z_all, int C, const nb200_tile_config* cfg, int scale, int offset,
                                        int tile_size, int blend_size, float* out, void* stream) {
+    NB_CHECK(cfg, "null pointer");
+    return nb200::tile_gather_blend_rows(z_all, C, cfg, scale, offset, tile_size, blend_size, out, 0, cfg->y_h, stream);
+}
+
+// rows [y0, y1) of the blended output; every tile covering those rows must already be in z_all
+int nb200::tile_gather_blend_rows(const void* z_all, int C, const nb200_tile_config* cfg, int scale, int offset, int tile_size,
+                                  int blend_size, float* out, int y0, int y1, void* stream) {
     NB_CHECK(z_all && cfg && out, "null pointer");
+    NB_CHECK(0 <= y0 && y0 < y1 && y1 <= cfg->y_h, "bad row range");
     NB_CHECK(blend_size >= 0 && blend_size <= 64, "blend_size out of range");
     BlendParams p;
     p.z = (const __half*)z_all;
@@ -181,17 +189,20 @@ extern "C" int nb200_tile_gather_blend(const void* z_all, int C, const nb200_til
     p.y_h = cfg->y_h; p.y_w = cfg->y_w; p.h_blocks = cfg->h_blocks; p.w_blocks = cfg->w_blocks;
     p.step_out = cfg->output_tile_step;
     p.blend = blend_size;
+    p.y0 = y0;
     NB_CHECK(p.S > 0 && p.S - p.step_out <= p.step_out, "tile overlap larger than the tile step is not supported");
     for (int d = 0; d < blend_size; ++d) {
         // ring index i = blend-1-d (outermost ring is added last); value = 1 - (1/(blend+1))*(i+1)
         const int i = blend_size - 1 - d;
         p.ring[d] = (float)(1.0 - (1.0 / (blend_size + 1)) * (i + 1));
     }
-    ProfScope ps((cudaStream_t)stream, PC_BLEND, (double)C * p.y_h * p.y_w * 4 + (double)p.h_blocks * p.w_blocks * C * p.S * p.S * 2);
+    const double frac = (double)(y1 - y0) / p.y_h;
+    ProfScope ps((cudaStream_t)stream, PC_BLEND,
+                 frac * ((double)C * p.y_h * p.y_w * 4 + (double)p.h_blocks * p.w_blocks * C * p.S * p.S * 2));
     if (p.y_w % 4 == 0 && p.step_out % 4 == 0 && p.S % 4 == 0 && ((uintptr_t)out & 15) == 0)
-        tile_gather_blend4_kernel<<<dim3(cdiv(p.y_w / 4, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
+        tile_gather_blend4_kernel<<<dim3(cdiv(p.y_w / 4, 256), y1 - y0), 256, 0, (cudaStream_t)stream>>>(p);
     else
-        tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), p.y_h), 256, 0, (cudaStream_t)stream>>>(p);
+        tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), y1 - y0), 256, 0, (cudaStream_t)stream>>>(p);
     NB_LAUNCHED();
     return 0;
 }

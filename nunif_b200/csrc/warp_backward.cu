@@ -178,6 +178,147 @@ __global__ void __launch_bounds__(256) backward_warp_kernel(BwParams p) {
     }
 }
 
+// Row-staged variant (the production path): one CTA per (row, batch).  The CTA first stages
+//   * the three colour rows in shared memory (coalesced 16 B loads, one replicated pad pixel so tap xa+1 needs
+//     no clamp), and
+//   * a per-depth-column table {gx_left(i0), gx_right(i0), gx_left(i1), gx_right(i1)} = mesh_x -/+ delta*scale
+//     of the two depth rows this output row interpolates between (backward_warp.py:68 evaluated once per
+//     depth column instead of once per output pixel),
+// then every thread produces 4 consecutive pixels of both eyes from shared memory only.  Against the
+// gather-from-global kernel above this removes the 64-bit address arithmetic (30% of its issue slots) and the
+// per-pixel depth loads; the kernel is then bounded by its HBM stores.
+struct __align__(16) GridTab { float l0, r0, l1, r1; };
+
+template <int COMPOSE>
+__global__ void __launch_bounds__(256) backward_warp_row_kernel(BwParams p, int S, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char bw_smem[];
+    GridTab* gt = reinterpret_cast<GridTab*>(bw_smem);          // [w + 1]
+    float* srow = reinterpret_cast<float*>(gt + (p.w + 1));     // [3][S], S >= W + 1, S % 4 == 0
+    const int y = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const size_t plane = (size_t)p.H * p.W;
+    const float* __restrict__ crow = p.c + ((size_t)b * 3 * p.H + y) * p.W;
+    const float* __restrict__ dep = p.depth + (size_t)b * p.h * p.w;
+
+    const bool same = (p.h == p.H) && (p.w == p.W);
+    int i0 = y, i1 = y;
+    float ly1 = 0.f;
+    if (!same) {
+        float srcy = p.sy * (float)y;
+        i0 = min((int)srcy, p.h - 1);
+        i1 = min(i0 + 1, p.h - 1);
+        ly1 = srcy - (float)i0;
+    }
+    const float ly0 = 1.f - ly1;
+
+    if (vec_ok) {
+        const int w4 = p.W >> 2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4* src = reinterpret_cast<const float4*>(crow + k * plane);
+            float4* dst = reinterpret_cast<float4*>(srow + k * S);
+            for (int i = tid; i < w4; i += 256) dst[i] = __ldg(src + i);
+        }
+    } else {
+        for (int k = 0; k < 3; ++k)
+            for (int i = tid; i < p.W; i += 256) srow[k * S + i] = __ldg(crow + k * plane + i);
+    }
+    for (int j = tid; j <= p.w; j += 256) {
+        const int jj = min(j, p.w - 1);
+        const float lx = linspace_m1_1(jj, p.w, p.step_x);
+        const float is0 = __fsub_rn(__fmul_rn(__ldg(dep + (size_t)i0 * p.w + jj), p.shift), p.shift_conv);
+        const float is1 = __fsub_rn(__fmul_rn(__ldg(dep + (size_t)i1 * p.w + jj), p.shift), p.shift_conv);
+        const float d0 = __fmul_rn(is0, p.delta_scale), d1 = __fmul_rn(is1, p.delta_scale);
+        GridTab t;
+        t.l0 = __fsub_rn(lx, d0); t.r0 = __fadd_rn(lx, d0);
+        t.l1 = __fsub_rn(lx, d1); t.r1 = __fadd_rn(lx, d1);
+        gt[j] = t;
+    }
+    __syncthreads();
+    if (tid < 3) srow[tid * S + p.W] = srow[tid * S + p.W - 1];
+    __syncthreads();
+
+    const float wm1 = (float)(p.W - 1);
+    const int ow = (COMPOSE == NB200_COMPOSE_SBS) ? 2 * p.W : p.W;
+    const size_t oplane = (size_t)p.H * ow;
+    float* lrow = p.left + ((size_t)b * 3 * p.H + y) * ow;
+    float* rrow = (COMPOSE == NB200_COMPOSE_SBS) ? lrow + p.W
+                  : (COMPOSE == NB200_COMPOSE_NONE ? p.right + ((size_t)b * 3 * p.H + y) * ow : nullptr);
+
+    for (int x0 = tid * 4; x0 < p.W; x0 += 1024) {
+        float outl[4][3], outr[4][3];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int x = min(x0 + v, p.W - 1);
+            const float srcx = p.sx * (float)x;
+            const int j0 = min((int)srcx, p.w - 1);
+            const float lx1 = srcx - (float)j0, lx0 = 1.f - lx1;
+            const float4 t0 = *reinterpret_cast<const float4*>(gt + j0);
+            const float4 t1 = *reinterpret_cast<const float4*>(gt + j0 + 1);
+            const float gl = ly0 * (lx0 * t0.x + lx1 * t1.x) + ly1 * (lx0 * t0.z + lx1 * t1.z);
+            const float gr = ly0 * (lx0 * t0.y + lx1 * t1.y) + ly1 * (lx0 * t0.w + lx1 * t1.w);
+#pragma unroll
+            for (int eye = 0; eye < 2; ++eye) {
+                float* o = eye == 0 ? outl[v] : outr[v];
+                const bool do_warp = eye == 0 ? p.warp_left : p.warp_right;
+                if (!do_warp) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) o[k] = srow[k * S + x];
+                    continue;
+                }
+                const float g = eye == 0 ? gl : gr;
+                float ix = ((g + 1.f) * 0.5f) * wm1;       // grid_sampler_unnormalize (align_corners)
+                ix = fminf(wm1, fmaxf(ix, 0.f));           // border padding
+                const float fx = floorf(ix);
+                const float wb = ix - fx, wa = (fx + 1.f) - ix;
+                const float* sp = srow + (int)fx;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o[k] = __saturatef(sp[k * S] * wa + sp[k * S + 1] * wb);
+            }
+        }
+        if (COMPOSE == NB200_COMPOSE_ANAGLYPH_DUBOIS) {
+            float res[4][3];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dubois_px(outl[v], outr[v], true, res[v]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (vec_ok) {
+                    *reinterpret_cast<float4*>(lrow + k * oplane + x0) = make_float4(res[0][k], res[1][k], res[2][k], res[3][k]);
+                } else {
+                    for (int v = 0; v < 4; ++v)
+                        if (x0 + v < p.W) lrow[k * oplane + x0 + v] = res[v][k];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (vec_ok) {
+                    __stcs(reinterpret_cast<float4*>(lrow + k * oplane + x0), make_float4(outl[0][k], outl[1][k], outl[2][k], outl[3][k]));
+                    __stcs(reinterpret_cast<float4*>(rrow + k * oplane + x0), make_float4(outr[0][k], outr[1][k], outr[2][k], outr[3][k]));
+                } else {
+                    for (int v = 0; v < 4; ++v)
+                        if (x0 + v < p.W) {
+                            lrow[k * oplane + x0 + v] = outl[v][k];
+                            rrow[k * oplane + x0 + v] = outr[v][k];
+                        }
+                }
+            }
+        }
+    }
+}
+
+extern int g_tune[8];  // gemm.cu; [3] != 0 forces the gather-from-global kernel (tests)
+
+template <int COMPOSE>
+static int launch_bw_row(const BwParams& p, size_t smem, int S, int vec_ok, cudaStream_t st) {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        NB_CUDA(cudaFuncSetAttribute(backward_warp_row_kernel<COMPOSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    backward_warp_row_kernel<COMPOSE><<<dim3(p.H, p.B), 256, smem, st>>>(p, S, vec_ok);
+    return 0;
+}
+
 __global__ void __launch_bounds__(256) anaglyph_dubois_kernel(const float* __restrict__ l, const float* __restrict__ r,
                                                                float* __restrict__ out, size_t plane, size_t total,
                                                                int clip_before) {
@@ -226,6 +367,22 @@ extern "C" int nb200_backward_warp(const float* c, const float* depth, int B, in
     cudaStream_t st = (cudaStream_t)stream;
     // algorithmic bytes: 3 planes in + output planes + the depth map
     ProfScope ps(st, PC_WARP_BW, (double)B * H * W * 4 * (3 + (compose == NB200_COMPOSE_ANAGLYPH_DUBOIS ? 3 : 6)) + (double)B * h * w * 4);
+    const int S = (W + 1 + 3) & ~3;
+    const size_t smem = sizeof(GridTab) * (size_t)(w + 1) + sizeof(float) * 3 * (size_t)S;
+    if (smem <= 200 * 1024 && g_tune[3] == 0 && B <= 65535) {
+        const bool aligned = (((uintptr_t)c | (uintptr_t)left | (uintptr_t)(right ? right : left)) & 15) == 0;
+        const int vec_ok = (W % 4 == 0) && aligned;
+        int rc;
+        switch (compose) {
+            case NB200_COMPOSE_NONE: rc = launch_bw_row<NB200_COMPOSE_NONE>(p, smem, S, vec_ok, st); break;
+            case NB200_COMPOSE_SBS: rc = launch_bw_row<NB200_COMPOSE_SBS>(p, smem, S, vec_ok, st); break;
+            case NB200_COMPOSE_ANAGLYPH_DUBOIS: rc = launch_bw_row<NB200_COMPOSE_ANAGLYPH_DUBOIS>(p, smem, S, vec_ok, st); break;
+            default: return fail("nb200_backward_warp: unknown compose mode");
+        }
+        if (rc) return rc;
+        NB_LAUNCHED();
+        return 0;
+    }
     switch (compose) {
         case NB200_COMPOSE_NONE: backward_warp_kernel<NB200_COMPOSE_NONE, VEC><<<grid, block, 0, st>>>(p); break;
         case NB200_COMPOSE_SBS: backward_warp_kernel<NB200_COMPOSE_SBS, VEC><<<grid, block, 0, st>>>(p); break;

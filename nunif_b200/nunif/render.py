@@ -13,20 +13,41 @@ def create_config(x_size, scale, offset, tile_size, blend_size):
     return cfg.as_dict()
 
 
-def tiled_render(x, model, tile_size=None, batch_size=None, enable_amp=False):
-    """x: C,H,W float tensor on the model's device -> C,H*scale,W*scale, contiguous, clamped.
+def tiled_render(x, model, tile_size=None, batch_size=None, enable_amp=False, out=None):
+    """x: C,H,W float tensor -> C,H*scale,W*scale, contiguous, clamped.
 
-    The engine always runs the reference's CUDA numerics (fp16 autocast,
-    nunif/device.py:58-71), so ``enable_amp`` is accepted for signature parity only.
+    * x on the model's device: the result is a device tensor (render.py:8-19).
+    * x on the HOST (the reference accepts that too - SeamBlending moves each minibatch with ``.to(device)``,
+      seam_blending.py:94): ``nb200_tiled_render_host`` copies the frame in once and streams the blended output back
+      in bands of finished tile rows while later tile batches compute.  The result is a pinned host tensor
+      (``out`` if given: C,H*scale,W*scale float32, ideally pinned) that is complete when the current stream is;
+      call ``torch.cuda.current_stream().synchronize()`` before reading it.
+
+    The engine always runs the reference's CUDA numerics (fp16 autocast, nunif/device.py:58-71), so
+    ``enable_amp`` is accepted for signature parity only.
     """
     assert not torch.is_grad_enabled()                                # seam_blending.py:50
-    _lib.require_cuda(x, "x")
     assert x.ndim == 3 and x.shape[0] == 3
-    xf = x.float().contiguous()
-    C, H, W = xf.shape
     batch_size = batch_size or model.i2i_default_batch_size
     tile_size = model.find_valid_tile_size(tile_size)
-    out = torch.empty((C, H * model.i2i_scale, W * model.i2i_scale), device=x.device, dtype=torch.float32)
+    C, H, W = x.shape
+    oshape = (C, H * model.i2i_scale, W * model.i2i_scale)
+    if not x.is_cuda:
+        dev = model.device
+        xf = x.float().contiguous()
+        if out is None:
+            out = torch.empty(oshape, dtype=torch.float32, pin_memory=True)
+        assert (not out.is_cuda) and out.dtype == torch.float32 and tuple(out.shape) == oshape and out.is_contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nb200_tiled_render_host(model._h, _lib.ptr(xf), C, H, W, int(tile_size), int(batch_size),
+                                                          int(model._downscale), _lib.ptr(out), _lib.stream_ptr(dev)))
+            if not xf.is_pinned():
+                torch.cuda.current_stream(dev).synchronize()           # xf may be a temporary: keep it alive until read
+        return out
+    _lib.require_cuda(x, "x")
+    xf = x.float().contiguous()
+    if out is None:
+        out = torch.empty(oshape, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().nb200_tiled_render(model._h, _lib.ptr(xf), C, H, W, int(tile_size), int(batch_size),
                                                  int(model._downscale), _lib.ptr(out), _lib.stream_ptr(x.device)))

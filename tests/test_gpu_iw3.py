@@ -54,6 +54,26 @@ def test_backward_warp_1080p_properties():
     assert s["max"] < TOL and stats(r, ro)["max"] < TOL
 
 
+def test_backward_warp_row_staged_and_gather_kernels_agree():
+    """The row-staged production kernel and the gather-from-global fallback (used when a row does not fit shared
+    memory) implement the same formula; odd widths take the scalar load/store path of the row kernel."""
+    from nunif_b200 import _lib
+    from nunif_b200.iw3 import apply_divergence_grid_sample
+    for (H, W, h, w) in ((270, 480, 98, 170), (37, 101, 37, 101), (64, 258, 20, 33)):
+        c = synth.synth_image(5, 3, H, W).unsqueeze(0).repeat(2, 1, 1, 1).to(DEV)
+        d = synth.synth_depth(6, 2, h, w).to(DEV)
+        for compose in (0, 1, 2):
+            a = apply_divergence_grid_sample(c, d, 3.0, 0.4, "both", compose=compose)
+            _lib.lib().nb200_tune_set(3, 1)
+            try:
+                b = apply_divergence_grid_sample(c, d, 3.0, 0.4, "both", compose=compose)
+            finally:
+                _lib.lib().nb200_tune_set(3, 0)
+            a = torch.cat(a, 1) if isinstance(a, tuple) else a
+            b = torch.cat(b, 1) if isinstance(b, tuple) else b
+            assert stats(a, b)["max"] < 2e-5, (H, W, compose, stats(a, b))
+
+
 def test_forward_warp_golden_exact_fullres_depth():
     """With a full-resolution depth there is no resize in the path: results must be bit-exact."""
     from nunif_b200.iw3 import apply_divergence_forward_warp

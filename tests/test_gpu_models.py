@@ -121,6 +121,30 @@ def test_swin_tiled_render_golden():
     assert torch.equal(y4, y4b)  # batch size must not change the result
 
 
+def test_host_render_matches_device_render():
+    """nb200_tiled_render_host (band-pipelined D2H) must return exactly what the device render returns, for pinned and
+    pageable host buffers, for batch sizes that end mid tile-row, and when called back to back into the same buffer."""
+    from nunif_b200.nunif.models import create_model
+    from nunif_b200.nunif.render import tiled_render
+    m4 = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), DEV)
+    img = synth.synth_image(21, 3, 150, 230)
+    with torch.no_grad():
+        want = tiled_render(img.to(DEV), m4, tile_size=64, batch_size=4).cpu()
+        for bs in (1, 3, 4, 64):
+            got = tiled_render(img.pin_memory(), m4, tile_size=64, batch_size=bs)
+            torch.cuda.synchronize()
+            assert not got.is_cuda and torch.equal(got, want), bs
+        out = torch.full(want.shape, -1.0)                 # pageable
+        got = tiled_render(img, m4, tile_size=64, batch_size=5, out=out)
+        torch.cuda.synchronize()
+        assert got is out and torch.equal(out, want)
+        buf = torch.empty(want.shape).pin_memory()
+        for _ in range(3):
+            tiled_render(img.pin_memory(), m4, tile_size=64, batch_size=4, out=buf)
+        torch.cuda.synchronize()
+        assert torch.equal(buf, want)
+
+
 def test_blend_is_exact_given_tile_outputs():
     """The tiling engine alone (unfold + gather-blend) against the oracle's raster-order blend, feeding both the
     same per-tile outputs: integer path bit-exact, float blend within 1e-6."""
