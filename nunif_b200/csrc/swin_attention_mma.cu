@@ -19,6 +19,8 @@
 
 namespace nb200 {
 
+extern int g_tune[8];  // gemm.cu (nb200_tune_set)
+
 namespace {
 constexpr int WS = 6, WTOK = 36, WPAD = 48, HEADS = 6;
 
@@ -41,6 +43,151 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+constexpr int NKT = 5;   // key tiles of 8 columns covering the 36 keys (columns 36..39 are masked by the bias table)
+
+__device__ __forceinline__ void mma1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void ldmatrix_x1_trans(uint32_t& r0, const void* smem_row) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.trans.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
+}
+
+template <int D>
+struct AttnCtx {
+    __half* sq;
+    const int* sreg;
+    const float4* bf;
+    const __half* kbase[NKT];
+    const __half* vbase[3];
+    int hc, g, t4;
+    float scale;
+    bool boundary;
+};
+
+// One 16-row query tile of one head: S = Q K^T, bias/mask, base-2 softmax numerators, O = P V, normalise, stage.
+// LAST: query rows 32..35 only (accumulator rows g+8 are padding and are not evaluated).
+template <int D, bool LAST>
+__device__ __forceinline__ void attn_mtile(const AttnCtx<D>& cx, int mt) {
+    constexpr int C = D * HEADS, LD = C + 8;
+    constexpr uint32_t ONES = 0x3C003C00u;   // half2(1, 1)
+    constexpr int HL = LAST ? 1 : 2;         // accumulator row halves in use
+    const int g = cx.g, t4 = cx.t4, hc = cx.hc;
+    const int row0 = min(mt * 16 + g, WTOK - 1), row1 = min(mt * 16 + g + 8, WTOK - 1);
+    // ---- S = Q K^T
+    float s[NKT][4];
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[nt][r] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < D / 16; ++kt) {
+        uint32_t a[4];
+        const __half* p0 = cx.sq + row0 * LD + hc + kt * 16 + 2 * t4;
+        const __half* p1 = cx.sq + row1 * LD + hc + kt * 16 + 2 * t4;
+        a[0] = *reinterpret_cast<const uint32_t*>(p0);
+        a[1] = *reinterpret_cast<const uint32_t*>(p1);
+        a[2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) {
+            const __half* pk = cx.kbase[nt] + kt * 16;
+            mma16816(s[nt], a, *reinterpret_cast<const uint32_t*>(pk), *reinterpret_cast<const uint32_t*>(pk + 8));
+        }
+    }
+    // ---- scale + bias (+ mask).  element r of tile nt: row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1).
+    // bias_frag holds log2(e)*relative_position_bias in exactly this fragment order (padded keys = -1e30), so
+    // scale + bias + key padding is one FMA per element and the softmax runs in base 2.
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt) {
+        const float4 bv = __ldg(cx.bf + (mt * 6 + nt) * 32);
+        s[nt][0] = fmaf(s[nt][0], cx.scale, bv.x);
+        s[nt][1] = fmaf(s[nt][1], cx.scale, bv.y);
+        if (!LAST) {
+            s[nt][2] = fmaf(s[nt][2], cx.scale, bv.z);
+            s[nt][3] = fmaf(s[nt][3], cx.scale, bv.w);
+        }
+    }
+    if (cx.boundary) {  // -100 across regions (:193-209)
+        const int q0 = cx.sreg[row0], q1 = cx.sreg[row1];
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cr = cx.sreg[min(nt * 8 + 2 * t4 + e, WTOK - 1)];
+                if (cr != q0) s[nt][e] += -100.0f * 1.4426950408889634f;
+                if (!LAST && cr != q1) s[nt][2 + e] += -100.0f * 1.4426950408889634f;
+            }
+    }
+    // ---- softmax numerators (base 2).  The row sums come out of the P V product itself (a ones column appended to V),
+    // i.e. they are the sums of exactly the fp16 probabilities that multiply V; 1/sum is applied to the output rows.
+#pragma unroll
+    for (int hlf = 0; hlf < HL; ++hlf) {
+        float mx = -1e30f;
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * hlf], s[nt][2 * hlf + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float pe;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s[nt][2 * hlf + e] - mx));
+                s[nt][2 * hlf + e] = pe;
+            }
+    }
+    if (LAST) {
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) s[nt][2] = s[nt][3] = 0.f;
+    }
+    // ---- O = P V  (P in fp16, un-normalised: values in [0, 1]); osum = P 1
+    float o[D / 8][4], osum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[nt][r] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+        uint32_t a[4];
+        a[0] = pack_half2(s[2 * kt][0], s[2 * kt][1]);
+        a[1] = pack_half2(s[2 * kt][2], s[2 * kt][3]);
+        a[2] = pack_half2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+        a[3] = pack_half2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+        mma16816(osum, a, ONES, ONES);
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt) {
+            uint32_t b0, b1;
+            ldmatrix_x2_trans(b0, b1, cx.vbase[kt] + nt * 8);
+            mma16816(o[nt], a, b0, b1);
+        }
+    }
+    {
+        const uint32_t a0 = pack_half2(s[4][0], s[4][1]), a1 = pack_half2(s[4][2], s[4][3]);
+        mma1688(osum, a0, a1, ONES);
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt) {
+            uint32_t b0;
+            ldmatrix_x1_trans(b0, cx.vbase[2] + nt * 8);
+            mma1688(o[nt], a0, a1, b0);
+        }
+    }
+    const float inv0 = __fdividef(1.f, osum[0]);
+    const float inv1 = LAST ? 0.f : __fdividef(1.f, osum[2]);
+    // ---- stage this head's output columns into sq.  Each warp only ever reads and writes its own columns of
+    // rows [16*mt, 16*mt+16) here, and those q rows are dead once this m-tile's S is done.
+    __syncwarp();
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) {
+        if (!LAST || r0 < WTOK) *reinterpret_cast<uint32_t*>(cx.sq + r0 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (!LAST) *reinterpret_cast<uint32_t*>(cx.sq + r1 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
 }
 
 template <int D>
@@ -95,114 +242,21 @@ __global__ void __launch_bounds__(192, 4) window_attention_mma_kernel(const __ha
     const float scale = ((D == 16) ? 0.25f : 0.17677669529663687f) * 1.4426950408889634f;  // (C//heads)**-0.5 (:187) * log2(e)
     const bool boundary = shift > 0 && (wy == gridDim.x / nww - 1 || wx == nww - 1);  // only these windows mix mask regions
     const float4* bf = bias_frag + (size_t)head * (3 * 6 * 32) + lane;
-    // per-thread fragment base pointers (row clamps and column offsets resolved once)
-    const __half* kbase[6];
+    AttnCtx<D> cx;
+    cx.sq = sq; cx.sreg = sreg; cx.bf = bf; cx.hc = hc; cx.g = g; cx.t4 = t4; cx.scale = scale; cx.boundary = boundary;
+    // per-thread fragment base pointers (row clamps and column offsets resolved once).  36 keys = 4.5 n8 tiles: S uses
+    // 5 key tiles (40 columns), P V uses two k16 steps and one k8 step.
 #pragma unroll
-    for (int nt = 0; nt < 6; ++nt) kbase[nt] = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + 2 * t4;
-    const __half* vbase[3];
-#pragma unroll
-    for (int kt = 0; kt < 3; ++kt) vbase[kt] = sv + min(kt * 16 + (lane & 15), WTOK - 1) * LD + hc;
-    // One 16-row m-tile at a time (rows 0-15, 16-31, 32-47): keeps the live state at 24 + 4*D/8 accumulators so that
+    for (int nt = 0; nt < NKT; ++nt) cx.kbase[nt] = sk + min(nt * 8 + g, WTOK - 1) * LD + hc + 2 * t4;
+    cx.vbase[0] = sv + (lane & 15) * LD + hc;
+    cx.vbase[1] = sv + (16 + (lane & 15)) * LD + hc;
+    cx.vbase[2] = sv + min(32 + (lane & 7), WTOK - 1) * LD + hc;
+    // One 16-row m-tile at a time (rows 0-15, 16-31, 32-47): keeps the live state at 20 + 4*D/8 (+4) accumulators so that
     // 4 CTAs fit per SM; K / V fragments are re-read from shared memory per m-tile (cheap, conflict-free).
+    // The last tile holds query rows 32..35 only: its upper half (rows 40..47) is skipped.
 #pragma unroll 1
-    for (int mt = 0; mt < 3; ++mt) {
-        const int row0 = min(mt * 16 + g, WTOK - 1), row1 = min(mt * 16 + g + 8, WTOK - 1);
-        // ---- S = Q K^T
-        float s[6][4];
-#pragma unroll
-        for (int nt = 0; nt < 6; ++nt)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) s[nt][r] = 0.f;
-#pragma unroll
-        for (int kt = 0; kt < D / 16; ++kt) {
-            uint32_t a[4];
-            const __half* p0 = sq + row0 * LD + hc + kt * 16 + 2 * t4;
-            const __half* p1 = sq + row1 * LD + hc + kt * 16 + 2 * t4;
-            a[0] = *reinterpret_cast<const uint32_t*>(p0);
-            a[1] = *reinterpret_cast<const uint32_t*>(p1);
-            a[2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
-            a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
-#pragma unroll
-            for (int nt = 0; nt < 6; ++nt) {
-                const __half* pk = kbase[nt] + kt * 16;
-                mma16816(s[nt], a, *reinterpret_cast<const uint32_t*>(pk), *reinterpret_cast<const uint32_t*>(pk + 8));
-            }
-        }
-        // ---- scale + bias (+ mask).  element r of tile nt: row = mt*16 + g + 8*(r>>1), col = nt*8 + 2*t4 + (r&1).
-        // bias_frag holds log2(e)*relative_position_bias in exactly this fragment order (padded keys = -1e30), so
-        // scale + bias + key padding is one FMA per element and the softmax runs in base 2.
-#pragma unroll
-        for (int nt = 0; nt < 6; ++nt) {
-            const float4 bv = __ldg(bf + (mt * 6 + nt) * 32);
-            s[nt][0] = fmaf(s[nt][0], scale, bv.x);
-            s[nt][1] = fmaf(s[nt][1], scale, bv.y);
-            s[nt][2] = fmaf(s[nt][2], scale, bv.z);
-            s[nt][3] = fmaf(s[nt][3], scale, bv.w);
-        }
-        if (boundary) {  // -100 across regions (:193-209)
-            const int q0 = sreg[row0], q1 = sreg[row1];
-#pragma unroll
-            for (int nt = 0; nt < 6; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int cr = sreg[min(nt * 8 + 2 * t4 + e, WTOK - 1)];
-                    if (cr != q0) s[nt][e] += -100.0f * 1.4426950408889634f;
-                    if (cr != q1) s[nt][2 + e] += -100.0f * 1.4426950408889634f;
-                }
-        }
-        // ---- softmax numerators (base 2); the 1/sum factor is applied to the output rows
-        float inv[2];
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-            float mx = -1e30f;
-#pragma unroll
-            for (int nt = 0; nt < 6; ++nt) mx = fmaxf(mx, fmaxf(s[nt][2 * hlf], s[nt][2 * hlf + 1]));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            float sum = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < 6; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    float pe;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s[nt][2 * hlf + e] - mx));
-                    s[nt][2 * hlf + e] = pe;
-                    sum += pe;
-                }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            inv[hlf] = __fdividef(1.f, sum);
-        }
-        // ---- O = P V  (P in fp16, un-normalised: values in [0, 1])
-        float o[D / 8][4];
-#pragma unroll
-        for (int nt = 0; nt < D / 8; ++nt)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) o[nt][r] = 0.f;
-#pragma unroll
-        for (int kt = 0; kt < 3; ++kt) {
-            uint32_t a[4];
-            a[0] = pack_half2(s[2 * kt][0], s[2 * kt][1]);
-            a[1] = pack_half2(s[2 * kt][2], s[2 * kt][3]);
-            a[2] = pack_half2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-            a[3] = pack_half2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
-#pragma unroll
-            for (int nt = 0; nt < D / 8; ++nt) {
-                uint32_t b0, b1;
-                ldmatrix_x2_trans(b0, b1, vbase[kt] + nt * 8);
-                mma16816(o[nt], a, b0, b1);
-            }
-        }
-        // ---- stage this head's output columns into sq.  Each warp only ever reads and writes its own columns of
-        // rows [16*mt, 16*mt+16) here, and those q rows are dead once this m-tile's S is done.
-        __syncwarp();
-        const int r0 = mt * 16 + g, r1 = r0 + 8;
-#pragma unroll
-        for (int nt = 0; nt < D / 8; ++nt) {
-            if (r0 < WTOK) *reinterpret_cast<uint32_t*>(sq + r0 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[nt][0] * inv[0], o[nt][1] * inv[0]);
-            if (r1 < WTOK) *reinterpret_cast<uint32_t*>(sq + r1 * LD + hc + nt * 8 + 2 * t4) = pack_half2(o[nt][2] * inv[1], o[nt][3] * inv[1]);
-        }
-    }
+    for (int mt = 0; mt < 2; ++mt) attn_mtile<D, false>(cx, mt);
+    attn_mtile<D, true>(cx, 2);
     __syncthreads();
     for (int t = rg; t < WTOK; t += RG)
         *reinterpret_cast<uint4*>(out + (size_t)stok[t] * C + vv * 8) = *reinterpret_cast<const uint4*>(sq + t * LD + vv * 8);
@@ -250,20 +304,24 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_
     if (WS >= H) shift = 0;  // torchvision :151-155
     dim3 grid((H / WS) * (W / WS), B);
     ProfScope ps(st, PC_ATTN, (double)B * H * W * C * 4 * 2, (double)B * H * W * C * 3 * 2, (double)B * H * W * C * 2);  // q,k,v in; out
+    // shared-memory carveout: just enough for the 4 resident CTAs, the rest stays L1 (the per-head bias fragments,
+    // 55 KB per layer, are re-read by every window and should hit there).  g_tune[6] overrides the percentage.
     if (C == 96) {
-        static bool cfg = false;
-        if (!cfg) {
+        static int cfg = -1;
+        const int want = g_tune[6] > 0 ? g_tune[6] : 44;
+        if (cfg != want) {
             NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>()));
-            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            cfg = true;
+            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
+            cfg = want;
         }
         window_attention_mma_kernel<16><<<grid, 192, attn_smem_bytes<16>(), st>>>(qkv, bias_table, out, H, W, shift, plane);
     } else {
-        static bool cfg = false;
-        if (!cfg) {
+        static int cfg = -1;
+        const int want = g_tune[6] > 0 ? g_tune[6] : 86;
+        if (cfg != want) {
             NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<32>()));
-            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            cfg = true;
+            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
+            cfg = want;
         }
         window_attention_mma_kernel<32><<<grid, 192, attn_smem_bytes<32>(), st>>>(qkv, bias_table, out, H, W, shift, plane);
     }

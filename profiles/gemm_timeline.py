@@ -11,7 +11,10 @@ dev = "cuda:0"
 T = 921600
 shape = sys.argv[1] if len(sys.argv) > 1 else "qkv"
 K, N, act, use_res = {"qkv": (192, 576, 0, False), "proj": (192, 192, 0, True), "fc1": (192, 384, 2, False),
-                      "toimg": (192, 48, 0, False), "fc2": (384, 192, 0, True)}[shape]
+                      "toimg": (192, 48, 0, False), "fc2": (384, 192, 0, True), "fc1_96": (96, 192, 2, False),
+                      "qkv96": (96, 288, 0, False), "proj96": (96, 96, 0, True), "fc2_96": (192, 96, 0, True)}[shape]
+if len(sys.argv) > 2:
+    lib.nb200_tune_set(4, int(sys.argv[2]))   # forced BLOCK_N
 A = torch.randn(T, K, device=dev).half()
 W = (torch.randn(N, K, device=dev) / K ** 0.5).half()
 b = torch.randn(N, device=dev)
@@ -37,9 +40,16 @@ names = {1: "prod:slot_free", 2: "mma:acc_free", 3: "mma:a_full", 4: "epi:acc_fu
          7: "epi:fence_done", 8: "epi:after_bar", 9: "epi:leader_done"}
 for base, role in ((0, "PROD"), (1024, "MMA"), (2048, "QUAD0"), (3072, "QUAD1")):
     ev = [(int(x) >> 56, (int(x) & ((1 << 56) - 1)) - t0) for x in v[base:base + 1024] if x]
-    print(f"== {role}: {len(ev)} events (first 60)")
+    print(f"== {role}: {len(ev)} events (first 24)")
+    # steady-state mean gap BEFORE each event type (second half of the record)
+    half = ev[len(ev) // 2:]
+    gaps = {}
+    for (e0, c0), (e1, c1) in zip(half[:-1], half[1:]):
+        gaps.setdefault(names.get(e1, e1), []).append(c1 - c0)
+    print("   steady mean clk before event:", {k: round(sum(g) / len(g)) for k, g in gaps.items()},
+          "span/event-cycle:", round((half[-1][1] - half[0][1]) / max(1, sum(1 for e, _ in half if e == half[0][0]))))
     prev = 0
-    for e, c in ev[:60]:
+    for e, c in ev[:24]:
         print(f"   {names.get(e, e):16s} t={c:8d}  (+{c - prev})")
         prev = c
     if len(ev) > 200:
