@@ -296,15 +296,18 @@ def run_b200(args):
                      "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
                      "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs (copy)",
                      "note": "Swin Linears have 96-144 FLOP/B < the 210 FLOP/B ridge: HBM-bound. achieved = algorithmic bytes "
-                             "(activations in + residual + out, weights once) / event time. frac_of_mix_floor uses the measured "
-                             "write-only (3.92 TB/s) and read-only (6.2 TB/s) limits per launch (profiles/r1/hbm_microbench.json)",
-                     "frac_of_mix_floor": gemm["hbm_floor_ms"] / gemm["ms"] if gemm["ms"] else None,
+                             "(activations in + residual + out, weights once) / event time over all GEMM launches of the profiled frame. "
+                             "Streaming kernels on this pool reach 6.7-7.4 TB/s for any read:write mix and the GEMM's own TMA box "
+                             "pattern 6.0 (store) / 6.9 (load) TB/s without math (profiles/r1/hbm_mix.json, tma_pattern.json)",
                      "tensor_tflops": ach, "tensor_peak_tflops": peak_tf, "tensor_frac": ach / peak_tf if peak_tf else None,
                      "launches": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
-                     "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None, "traffic": None},
+                     "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None,
+                     # ncu --set full of the largest launch class (qkv Linear of a 16-tile batch, M=921600 K=192 N=576):
+                     # dram__bytes_read.sum + dram__bytes_write.sum = 354.2 MB + 1003.3 MB against 1415.7 MB algorithmic,
+                     # i.e. no re-reads (profiles/r1/gemm_persistent_v1_qkv_ncu_full_summary.csv)
+                     "traffic": 1.3575e9, "traffic_algorithmic": 1.4157e9},
         "roofline_attention": {"bound": "hbm", "kernel": "window_attention_mma_kernel", "achieved": attn_gbs, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": attn_gbs / peaks["hbm_gbs"],
-                               "frac_of_mix_floor": attn["hbm_floor_ms"] / attn["ms"] if attn["ms"] else None,
                                "share_of_step": attn["ms"] / total_prof_ms if total_prof_ms else None},
         "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }

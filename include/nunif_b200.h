@@ -118,6 +118,21 @@ int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, int W, int 
 int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, int W, int tile_size,
                             int batch_size, int downscale, float* out_host, void* stream);
 
+/* AlphaBorderPadding.forward (nunif/utils/alpha.py:32-57): rgb [3][H][W], alpha [1][H][W] fp32 ->
+ * out [3][H][W]: transparent pixels are filled from their opaque neighbours, `offset` rounds
+ * (offset = the model's i2i_offset, waifu2x/utils.py:271), then clamped to [0,1]. */
+size_t nb200_alpha_border_padding_workspace(int H, int W);
+int nb200_alpha_border_padding(const float* rgb, const float* alpha, int H, int W, int offset,
+                               float* out, void* workspace, void* stream);
+
+/* tta_split (nunif/transforms/tta.py:20-33): view k in 0..7 of x [C][H][W]
+ * (identity, hflip, vflip, vflip+hflip, then the same four of rot90) -> out [C][H][W] (k<4)
+ * or [C][W][H] (k>=4).  tta_merge (:36-48): views[k] is the render of view k, i.e.
+ * [C][H][W] for k<4 and [C][W][H] for k>=4 (H, W = merged size) -> out = clamp(mean of the
+ * inverse-transformed views).  `views` is a host array of 8 device pointers. */
+int nb200_tta_transform(const float* x, int C, int H, int W, int k, float* out, void* stream);
+int nb200_tta_merge(const float* const* views, int C, int H, int W, float* out, void* stream);
+
 /* ------------------------------------------------------------------ *
  * Path B: iw3 depth post-processing and stereo warps
  * ------------------------------------------------------------------ */
@@ -188,6 +203,20 @@ int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci, int Cin, i
  * -> out [B][H][W][C] fp16; bias_table fp32 [121][6]. */
 int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B,
                                int H, int W, int C, int heads, int shift, void* stream);
+
+/* Frame-edge conversions (nunif/utils/video.py:218-223 to_tensor, :236-246 from_tensor,
+ * iw3/utils.py:274-289 hwc_to_chw_float): x [B][H][W][3] uint8 (bits=8) or uint16 (bits=16)
+ * <-> [B][3][H][W] fp32 in [0,1]; the fp32 -> integer direction rounds half to even. */
+int nb200_hwc_to_chw_f32(const void* x, int bits, int B, int H, int W, float* out, void* stream);
+int nb200_chw_f32_to_hwc(const float* x, int bits, int B, int H, int W, void* out, void* stream);
+
+/* DepthAnything batch_preprocess (iw3/depth_anything_model.py:69-110): size rule (host,
+ * integers) and the fused antialiased-bilinear resize + clamp + ImageNet normalise:
+ * x [B][3][H][W] fp32 in [0,1] -> out [B][3][new_h][new_w] fp32. */
+int nb200_da_preprocess_size(int H, int W, int lower_bound, int max_aspect_ratio,
+                             int limit_resolution, int* new_h, int* new_w);
+int nb200_da_preprocess(const float* x, int B, int H, int W, int new_h, int new_w, float* out,
+                        void* stream);
 
 /* Kernel-class device timing (CUDA events around every launch of this library) used by
  * bench.py for the live roofline figure.  report writes a JSON object

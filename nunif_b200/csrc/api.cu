@@ -13,7 +13,9 @@ std::atomic<int> g_prof_enabled{0};
 
 struct ProfRec { cudaEvent_t a, b; int cat; double work, rb, wb; };
 // measured HBM rates of this pool (profiles/r1/hbm_microbench.json): copy, write-only, read-only, bytes/s
-static double g_bw_copy = 6.6e12, g_bw_write = 3.92e12, g_bw_read = 6.2e12;
+// streaming-kernel ceilings measured on this pool (profiles/r1/hbm_mix.json): copy 6.6-6.7, write-only 7.4, read-heavy 7.0 TB/s.
+// (An earlier 3.92 TB/s "write-only limit" was torch's fill_ kernel, not the HBM.)
+static double g_bw_copy = 6.6e12, g_bw_write = 7.4e12, g_bw_read = 7.0e12;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;

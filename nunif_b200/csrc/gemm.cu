@@ -244,7 +244,11 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         }
         // epilogue-heavy launches (GELU): narrower tiles give a 4-deep TMEM accumulator ring, so the quads
         // rarely wait for the MMA (profiles/r1/timeline_fc1_*.txt); chunks never straddle a split plane (cout % 64 == 0)
-        const int forced = g_tune[4] > 0 ? g_tune[4] : ((g.act == ACT_GELU && g_tune[5] == 0) ? 128 : 0);
+        // residual launches with K = N = 192 (the Swin proj Linear): 64-wide tiles keep 24 KB of weights resident instead
+        // of 72 KB, which doubles the activation ring (3 -> 6 stages) next to the residual/output staging;
+        // profiles/r1/gemm_bench_v4.json: 197 -> 177 us
+        const bool narrow_res = g.res && g.N == 192 && p.taps * ktap == 192 && g_tune[5] == 0;
+        const int forced = g_tune[4] > 0 ? g_tune[4] : ((g.act == ACT_GELU && g_tune[5] == 0) ? 128 : (narrow_res ? 64 : 0));
         if (forced > 0 && g.N % forced == 0 && !shuf) {
             const int w = (forced % 64 == 0) ? 64 : ((forced % 32 == 0) ? 32 : 16);
             if (!split || g.cout % w == 0) { bn = forced; cw = w; }

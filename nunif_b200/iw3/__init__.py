@@ -12,3 +12,5 @@ from .dilation import dilate_edge, edge_dilation_parse, edge_dilation_is_enabled
 from .depth_scaler import minmax_normalize  # noqa: F401
 from .anaglyph import apply_anaglyph_redcyan  # noqa: F401
 from .stereo import stereo_sbs  # noqa: F401
+from .frames import hwc_to_chw_float, chw_float_to_hwc  # noqa: F401
+from .depth_anything_preprocess import batch_preprocess, preprocess_size  # noqa: F401

@@ -4,6 +4,9 @@ from os import path
 import torch
 from ..nunif.models import load_model
 from ..nunif.render import tiled_render
+from ..nunif.alpha import AlphaBorderPadding
+from ..nunif.tta import tta_split, tta_merge
+import torch.nn.functional as F
 from .. import _lib
 
 
@@ -14,6 +17,7 @@ class Waifu2x():
         self.noise_models = [None] * 4
         self.noise_scale_models = [None] * 4
         self.noise_scale4x_models = [None] * 4
+        self.alpha_pad = AlphaBorderPadding()
         # nunif/device.py:12-32 create_device: gpus[0] < 0 means CPU in the reference; this engine is CUDA-only
         gpu = gpus[0] if isinstance(gpus, (list, tuple)) else gpus
         if isinstance(gpu, int) and gpu < 0:
@@ -153,19 +157,30 @@ class Waifu2x():
         x = x.to(self.device)
         blank_alpha = True
         if alpha is not None:
+            # check all 1 alpha channel (waifu2x/utils.py:266-268)
             blank_alpha = bool(torch.equal(alpha, torch.ones(alpha.shape, device=alpha.device, dtype=alpha.dtype)))
         if alpha is not None and not blank_alpha:
-            raise NotImplementedError(
-                "non-opaque alpha (AlphaBorderPadding, nunif/utils/alpha.py:32-57) is a 'next' row of the "
-                "hot-path scope (SURVEY.md 8f rank 3) and is not implemented by the B200 engine yet")
+            alpha = alpha.to(self.device)
+            x = self.alpha_pad(x, alpha, self._model(method, noise_level).i2i_offset)       # :269-271
         if tta:
-            raise NotImplementedError("tta=True (nunif/transforms/tta.py) is a 'next' row of the hot-path scope")
-        rgb = self.render(x, method, noise_level, tile_size, batch_size, enable_amp)
+            rgb = tta_merge([self.render(xx, method, noise_level, tile_size, batch_size, enable_amp)
+                             for xx in tta_split(x)])                                         # :272-275
+        else:
+            rgb = self.render(x, method, noise_level, tile_size, batch_size, enable_amp)
         rgb = rgb.to(output_device)
         if alpha is not None and method in ("scale", "noise_scale", "scale4x", "noise_scale4x"):
-            # all-ones alpha: nearest upscale of ones is ones (waifu2x/utils.py:292-294)
             s = 4 if method in {"scale4x", "noise_scale4x"} else 2
-            alpha = torch.ones((1, alpha.shape[1] * s, alpha.shape[2] * s), dtype=alpha.dtype, device=output_device)
-        elif alpha is not None:
+            if not blank_alpha:
+                model = self.scale4x_model if method in {"scale4x", "noise_scale4x"} else self.scale_model
+                if model is not None:
+                    # second render pass on the alpha plane (:282-287)
+                    alpha = alpha.expand(3, alpha.shape[1], alpha.shape[2])
+                    alpha = tiled_render(alpha, model, tile_size=tile_size, batch_size=batch_size,
+                                         enable_amp=enable_amp).mean(0, keepdim=True)
+                else:
+                    alpha = F.interpolate(alpha.unsqueeze(0), scale_factor=s, mode="bilinear").squeeze(0)   # :288-291
+            else:
+                # all-ones alpha: the nearest upscale of ones is ones (:292-294)
+                alpha = torch.ones((1, alpha.shape[1] * s, alpha.shape[2] * s), dtype=alpha.dtype, device=output_device)
             alpha = alpha.to(output_device)
         return rgb, alpha

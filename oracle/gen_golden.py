@@ -157,12 +157,86 @@ def gen_iw3():
     save("anaglyph", **out)
 
 
+def gen_alpha_tta():
+    """AlphaBorderPadding (nunif/utils/alpha.py) and tta_split/tta_merge (nunif/transforms/tta.py)."""
+    from nunif.utils.alpha import AlphaBorderPadding
+    from nunif.transforms.tta import tta_split, tta_merge
+    g = torch.Generator().manual_seed(7)
+    H, W = 45, 61
+    rgb = torch.rand(3, H, W, generator=g)
+    # alpha: two opaque blobs with soft edges, a hole, and a fully transparent corner region
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    a = torch.clamp(1.3 - ((yy - 14) ** 2 + (xx - 18) ** 2).sqrt() / 9, 0, 1)
+    a = torch.maximum(a, torch.clamp(1.2 - ((yy - 33) ** 2 / 30 + (xx - 44) ** 2 / 90).sqrt(), 0, 1))
+    a[12:16, 16:20] = 0
+    alpha = a.unsqueeze(0)
+    pad = AlphaBorderPadding().eval()
+    out = {"rgb": rgb, "alpha": alpha}
+    for off in (0, 1, 8, 17, 36):
+        out[f"pad_{off}"] = pad(rgb, alpha, off)
+    x = torch.rand(3, 22, 31, generator=g)
+    views = tta_split(x)
+    for k, v in enumerate(views):
+        out[f"view_{k}"] = v.contiguous()
+    zs = [torch.rand(v.shape, generator=g) * 1.2 - 0.1 for v in views]
+    for k, z in enumerate(zs):
+        out[f"z_{k}"] = z
+    out["x"] = x
+    out["merged"] = tta_merge(zs)
+    out["merged_identity"] = tta_merge([v.clone() for v in views])
+    save("alpha_tta", **out)
+
+
+def gen_frames():
+    """Frame conversions (nunif/utils/video.py, iw3/utils.py:274-289) and DepthAnything batch_preprocess."""
+    # iw3/utils.py imports PyAV (absent in this image) at module scope, so the pure-tensor helper
+    # hwc_to_chw_float (iw3/utils.py:274-289) is executed from the reference source file without importing the module.
+    import ast
+    src = open("/root/reference/iw3/utils.py").read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "hwc_to_chw_float")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "/root/reference/iw3/utils.py", "exec"), ns)
+    hwc_to_chw_float = ns["hwc_to_chw_float"]
+    from iw3.depth_anything_model import batch_preprocess
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    u8 = torch.randint(0, 256, (2, 37, 53, 3), generator=g, dtype=torch.uint8)
+    u16 = torch.randint(0, 65536, (37, 53, 3), generator=g, dtype=torch.int32).to(torch.uint16)
+    out["u8"], out["u16"] = u8, u16.view(torch.int16)
+    out["u8_f"] = hwc_to_chw_float(u8, "cpu")
+    out["u16_f"] = hwc_to_chw_float(u16, "cpu")
+    f = torch.rand(3, 41, 29, generator=g)
+    f[0, 0, :8] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 0.0, 1.0, 0.49999 / 255, 127.5 / 255])
+    out["f"] = f
+    # from_tensor's tensor part (video.py:244)
+    out["f_u8"] = (f.permute(1, 2, 0).contiguous() * 255.0).round_().to(torch.uint8)
+    out["f_u16"] = (f.permute(1, 2, 0).contiguous() * 65535.0).round_().to(torch.uint16).view(torch.int16)
+    x = torch.rand(2, 3, 135, 240, generator=g)
+    out["x"] = x
+    out["prep_126"] = batch_preprocess(x.clone(), lower_bound=126)
+    out["prep_98_limit"] = batch_preprocess(x.clone(), lower_bound=392, limit_resolution=True)
+    xt = torch.rand(1, 3, 300, 64, generator=g)   # tall: aspect cap + width floor
+    out["xt"] = xt
+    out["prep_tall"] = batch_preprocess(xt.clone(), lower_bound=70)
+    sizes = []
+    for (H, W) in ((1080, 1920), (2160, 3840), (720, 1280), (480, 854), (1920, 1080), (300, 3000), (100, 100), (393, 699)):
+        for lb, lim in ((392, False), (518, False), (392, True), (224, True)):
+            y = batch_preprocess(torch.zeros(1, 3, H, W), lower_bound=lb, limit_resolution=lim)
+            sizes.append((H, W, lb, int(lim), y.shape[2], y.shape[3]))
+    out["sizes"] = np.array(sizes, dtype=np.int64)
+    save("frames", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
         gen_models()
     if "iw3" in which:
         gen_iw3()
+    if "alpha_tta" in which:
+        gen_alpha_tta()
+    if "frames" in which:
+        gen_frames()

@@ -11,7 +11,7 @@ from nunif_b200 import _lib  # noqa: E402
 lib = _lib.lib()
 dev = "cuda:0"
 T = 921600
-COPY, WR, RD = 6.6e12, 3.92e12, 6.2e12   # profiles/r1/hbm_microbench.json
+COPY, WR, RD = 6.6e12, 7.4e12, 7.0e12   # streaming kernels, profiles/r1/hbm_mix.json (write-only 7.47, read+2 writes 6.86 TB/s)
 
 
 def gemm(A, W, bias, out, act=0, res=None):

@@ -12,7 +12,7 @@ from nunif_b200.iw3 import apply_divergence_grid_sample, apply_divergence_forwar
 lib = _lib.lib()
 dev = "cuda:0"
 H, W, h, w = 1080, 1920, 392, 686
-COPY, WR, RD = 6.6e12, 3.92e12, 6.2e12   # profiles/r1/hbm_microbench.json
+COPY, WR, RD = 6.6e12, 7.4e12, 7.0e12   # streaming kernels, profiles/r1/hbm_mix.json (write-only 7.47, read+2 writes 6.86 TB/s)
 
 
 def timeit(fn, iters=50):

@@ -79,3 +79,14 @@ def test_find_valid_tile_size_host():
         assert m_c.find_valid_tile_size(int(q)) == int(c)
         assert m_s.find_valid_tile_size(int(q)) == int(s)
     assert m_s.find_valid_tile_size(None) == 256
+
+
+def test_da_preprocess_size_host_rule_bit_exact():
+    """nb200_da_preprocess_size is host integer logic (depth_anything_model.py:69-101): check it against the sizes the
+    reference produced (tests/golden/frames.npz) without a GPU."""
+    from tests.util import load_golden
+    from nunif_b200.iw3.depth_anything_preprocess import preprocess_size
+    g = load_golden("frames")
+    for H, W, lb, lim, nh, nw in g["sizes"]:
+        assert preprocess_size(int(H), int(W), int(lb), 4, bool(lim)) == (int(nh), int(nw)), (H, W, lb, lim)
+    assert preprocess_size(1080, 1920) == (392, 686)

@@ -10,6 +10,7 @@ from oracle import seam_blending as osb
 from oracle import cunet as ocu
 from oracle import swin_unet as osw
 from oracle import iw3 as oiw
+from tests.util import load_golden
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 torch.set_grad_enabled(False)
@@ -164,3 +165,42 @@ def test_anaglyph():
     l, r = t(g["l"]), t(g["r"])
     assert maxdiff(oiw.dubois(l, r, True), g["dubois"]) < 1e-6
     assert maxdiff(oiw.dubois(l, r, False), g["dubois2"]) < 1e-6
+
+
+def test_alpha_border_padding_oracle_matches_reference():
+    from oracle import alpha_tta as oat
+    g = load_golden("alpha_tta")
+    for off in (0, 1, 8, 17, 36):
+        got = oat.alpha_border_padding(g["rgb"], g["alpha"], off)
+        # the reference sums its 3x3 box with a depthwise conv whose accumulation order is not specified
+        assert np.abs(got - g[f"pad_{off}"]).max() < 2e-6, off
+
+
+def test_tta_oracle_matches_reference():
+    from oracle import alpha_tta as oat
+    g = load_golden("alpha_tta")
+    views = oat.tta_split(g["x"])
+    for k in range(8):
+        assert np.array_equal(views[k], g[f"view_{k}"]), k
+    assert np.array_equal(oat.tta_merge([g[f"z_{k}"] for k in range(8)]), g["merged"])
+    assert np.abs(oat.tta_merge(list(views)) - g["merged_identity"]).max() == 0
+
+
+def test_frame_conversion_oracle_matches_reference():
+    from oracle import frames as ofr
+    g = load_golden("frames")
+    assert np.array_equal(ofr.hwc_to_chw_float(g["u8"]), g["u8_f"])
+    assert np.array_equal(ofr.hwc_to_chw_float(g["u16"].view(np.uint16)), g["u16_f"])
+    assert np.array_equal(ofr.chw_float_to_hwc(g["f"]), g["f_u8"])
+    assert np.array_equal(ofr.chw_float_to_hwc(g["f"], use_16bit=True), g["f_u16"].view(np.uint16))
+
+
+def test_da_preprocess_oracle_matches_reference():
+    from oracle import frames as ofr
+    g = load_golden("frames")
+    for H, W, lb, lim, nh, nw in g["sizes"]:
+        assert ofr.preprocess_size(int(H), int(W), int(lb), 4, bool(lim)) == (int(nh), int(nw)), (H, W, lb, lim)
+    # ATen's CPU kernel accumulates the separable passes in a different order: a few fp32 ulps
+    assert np.abs(ofr.batch_preprocess(g["x"], lower_bound=126) - g["prep_126"]).max() < 3e-6
+    assert np.abs(ofr.batch_preprocess(g["x"], lower_bound=392, limit_resolution=True) - g["prep_98_limit"]).max() < 3e-6
+    assert np.abs(ofr.batch_preprocess(g["xt"], lower_bound=70) - g["prep_tall"]).max() < 3e-6
