@@ -79,7 +79,10 @@ enum {
     NB200_MODEL_CUNET = 2,          /* waifu2x.cunet    (cunet.py:173-203)                */
     NB200_MODEL_SWIN_UNET_1X = 3,   /* waifu2x.swin_unet_1x (swin_unet.py:208-226)        */
     NB200_MODEL_SWIN_UNET_2X = 4,   /* waifu2x.swin_unet_2x (swin_unet.py:229-251)        */
-    NB200_MODEL_SWIN_UNET_4X = 5    /* waifu2x.swin_unet_4x (swin_unet.py:261-303)        */
+    NB200_MODEL_SWIN_UNET_4X = 5,   /* waifu2x.swin_unet_4x (swin_unet.py:261-303)        */
+    /* Depth-Anything-V2 ViT-S: third-party net the reference loads through torch.hub
+     * (iw3/depth_anything_model.py:223-230); state_dict keys `pretrained.*`, `depth_head.*` */
+    NB200_MODEL_DEPTH_ANYTHING_V2_S = 6
 };
 
 /* Create a model from named fp32 host tensors using the reference's state_dict
@@ -117,6 +120,12 @@ int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, int W, int 
  * seam_blending.py:94). */
 int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, int W, int tile_size,
                             int batch_size, int downscale, float* out_host, void* stream);
+
+/* DepthAnythingV2.forward as called by DepthAnythingModel._forward (iw3/depth_anything_model.py:113-119):
+ * x [B][3][H][W] fp32, ImageNet-normalised (nb200_da_preprocess), H and W multiples of 14
+ * -> depth [B][H][W] fp32 (relative inverse depth, larger = nearer). */
+int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth,
+                                 void* stream);
 
 /* AlphaBorderPadding.forward (nunif/utils/alpha.py:32-57): rgb [3][H][W], alpha [1][H][W] fp32 ->
  * out [3][H][W]: transparent pixels are filled from their opaque neighbours, `offset` rounds
@@ -187,7 +196,7 @@ int nb200_anaglyph_dubois(const float* l, const float* r, int B, int H, int W, i
 int nb200_depth_resize_aa(const float* depth, int B, int h, int w, int H, int W, float* out, void* stream);
 
 /* tcgen05 implicit GEMM on NHWC fp16 activations (csrc/gemm_tcgen05.cuh).
- * kind: 0 linear over flattened pixels, 1 linear with 2-D tiling, 2 conv3x3 valid,
+ * kind: 0 linear over flattened pixels, 1 linear with 2-D tiling, 2 conv3x3 valid (4 = conv3x3 zero-padded by 1),
  *       3 conv2x2 stride 2.  Wt: fp16 [N][taps*Cin] with K ordered (ky, kx, c).
  * act: 0 none, 1 LeakyReLU(0.1), 2 GELU(erf), 3 ReLU.
  * out_mode 1: N = 4*cout ordered (dy,dx,co), pixel-shuffle(2) scatter (ConvTranspose2d

@@ -56,7 +56,9 @@ struct DaPrepParams {
 __global__ void __launch_bounds__(128) da_preprocess_kernel(DaPrepParams p) {
     const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y, b = blockIdx.z;
     if (ox >= p.ow) return;
-    const float cy = p.sy * ((float)oy + 0.5f), cx = p.sx * ((float)ox + 0.5f);
+    // the centre is a rounded fp32 product in ATen; without _rn the compiler fuses it into the tap-offset subtraction
+    // below (fma), which shifts every weight by up to 1e-5
+    const float cy = __fmul_rn(p.sy, (float)oy + 0.5f), cx = __fmul_rn(p.sx, (float)ox + 0.5f);
     const int ymin = max(0, (int)(cy - p.supy + 0.5f)), ysize = min(p.H, (int)(cy + p.supy + 0.5f)) - ymin;
     const int xmin = max(0, (int)(cx - p.supx + 0.5f)), xsize = min(p.W, (int)(cx + p.supx + 0.5f)) - xmin;
     float wxs = 0.f, wys = 0.f;

@@ -193,9 +193,12 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         case CG_LINEAR_2D:
         case CG_CONV3: {
             const int kk = g.kind == CG_CONV3 ? 3 : 1;
-            p.B = g.B; p.Ho = g.Hi - (kk - 1); p.Wo = g.Wi - (kk - 1); p.TH = 8; p.TW = 16;
+            const int pad = g.kind == CG_CONV3 ? g.pad : 0;
+            NB_CHECK(pad == 0 || pad == 1, "conv3x3 padding must be 0 or 1");
+            p.B = g.B; p.Ho = g.Hi - (kk - 1) + 2 * pad; p.Wo = g.Wi - (kk - 1) + 2 * pad; p.TH = 8; p.TW = 16;
             p.taps = kk * kk; ktap = g.Cin;
-            for (int t = 0; t < p.taps; ++t) { p.tap_dy[t] = t / kk; p.tap_dx[t] = t % kk; p.tap_dyi[t] = 0; }
+            // pad: tap coordinates start at -1; tensor-map loads zero-fill everything outside [0, Wi) x [0, Hi)
+            for (int t = 0; t < p.taps; ++t) { p.tap_dy[t] = (int8_t)(t / kk - pad); p.tap_dx[t] = (int8_t)(t % kk - pad); p.tap_dyi[t] = 0; }
             dims[0] = g.Cin; dims[1] = g.Wi; dims[2] = 1; dims[3] = g.Hi; dims[4] = g.B;
             strides[0] = g.Ci * e; strides[1] = rs; strides[2] = rs;
             strides[3] = is;
@@ -318,7 +321,9 @@ extern "C" int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci,
                                    const void* res, int ldr, int res_H, int res_W, int res_cy, int res_cx,
                                    int res_before_act, void* stream) {
     ConvGemm g;
-    g.A = (const __half*)A; g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Cin = Cin; g.kind = kind;
+    g.A = (const __half*)A; g.B = B; g.Hi = Hi; g.Wi = Wi; g.Ci = Ci; g.Cin = Cin;
+    g.kind = kind == 4 ? CG_CONV3 : kind;   // 4 = 3x3 conv with zero padding 1
+    g.pad = kind == 4 ? 1 : 0;
     g.Wt = (const __half*)Wt; g.N = N; g.bias = bias; g.act = act; g.out = (__half*)out; g.ldo = ldo;
     g.out_mode = out_mode; g.cout = cout; g.res = (const __half*)res; g.ldr = ldr; g.res_H = res_H; g.res_W = res_W;
     g.res_cy = res_cy; g.res_cx = res_cx; g.res_before_act = res_before_act;

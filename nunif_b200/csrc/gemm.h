@@ -14,6 +14,7 @@ struct ConvGemm {
     long long a_row_stride = 0; // elements between image rows (0 = Wi*Ci); lets A be a cropped view
     long long a_img_stride = 0; // elements between images     (0 = Hi*a_row_stride)
     int kind = CG_LINEAR_FLAT;
+    int pad = 0;                // CG_CONV3: zero padding (0 = valid conv, 1 = 'same'); the halo comes from the TMA's out-of-bounds zero fill
     const __half* Wt = nullptr; // packed weights [N][taps*Cin_tap], K ordered (ky, kx, c)
     int N = 0;
     const float* bias = nullptr;

@@ -6,6 +6,7 @@
 #include "gemm_tcgen05.cuh"
 #include "swin_kernels.h"
 #include "cunet_kernels.h"
+#include "depth_kernels.h"
 #include "../../include/nunif_b200.h"
 #include <map>
 #include <vector>
@@ -178,6 +179,7 @@ struct SwinW {
 };
 
 struct CUNetW;  // cunet_model.inl
+struct DaW;     // depth_model.inl
 
 }  // namespace nb200
 
@@ -190,6 +192,7 @@ struct nb200_model {
     size_t blob_bytes = 0;
     SwinW sw;
     std::shared_ptr<CUNetW> cu;
+    std::shared_ptr<DaW> da;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
@@ -410,6 +413,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 }  // namespace nb200
 
 #include "cunet_model.inl"
+#include "depth_model.inl"
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -417,7 +421,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
                                   const int64_t* numel, int no_clip, nb200_model** out) {
     NB_CHECK(out && names && data && numel, "null pointer");
-    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_SWIN_UNET_4X, "unknown model kind");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_DEPTH_ANYTHING_V2_S, "unknown model kind");
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
@@ -442,6 +446,7 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
         case NB200_MODEL_SWIN_UNET_4X: pack_swin(pk, m->sw, 4); m->scale = 4; m->offset = 32; m->blend = 16; break;  // :267
         case NB200_MODEL_UPCUNET: m->cu = pack_cunet(pk, true); m->scale = 2; m->offset = 36; m->blend = 0; break;   // cunet.py:144
         case NB200_MODEL_CUNET: m->cu = pack_cunet(pk, false); m->scale = 1; m->offset = 28; m->blend = 0; break;    // cunet.py:178
+        case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk); m->scale = 1; break;
     }
     if (pk.err.empty())
         for (auto& kv : pk.src)
@@ -502,6 +507,7 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
     int scale, offset, blend, S;
     if (model_out_geometry(m, tile_size, downscale, &scale, &offset, &blend, &S)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
+    NB_CHECK(m->kind <= NB200_MODEL_SWIN_UNET_4X, "not an image-to-image model");
     if (m->kind >= NB200_MODEL_SWIN_UNET_1X) return swin_forward(m, st, (const __half*)x, n, tile_size, downscale, (__half*)z);
     return cunet_forward(m, st, (const __half*)x, n, tile_size, (__half*)z);
 }
@@ -596,4 +602,12 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     cudaFreeAsync(xb, st);
     cudaFreeAsync(zall, st);
     return rc;
+}
+
+// DepthAnythingV2.forward (what DepthAnythingModel._forward calls, iw3/depth_anything_model.py:113-119)
+extern "C" int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth, void* stream) {
+    NB_CHECK(m && x && depth, "null pointer");
+    NB_CHECK(m->kind == NB200_MODEL_DEPTH_ANYTHING_V2_S && m->da, "model is not a Depth-Anything network");
+    NB_CHECK(B > 0, "empty batch");
+    return depth_anything_forward(m, (cudaStream_t)stream, x, B, H, W, depth);
 }

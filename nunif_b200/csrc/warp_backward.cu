@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) backward_warp_kernel(BwParams p) {
     int i0 = y, i1 = y;
     float ly1 = 0.f;
     if (!same) {
-        float srcy = p.sy * (float)y;
+        float srcy = __fmul_rn(p.sy, (float)y);   // rounded like ATen's h1r (no fma into the lambda below)
         i0 = min((int)srcy, p.h - 1);
         i1 = min(i0 + 1, p.h - 1);
         ly1 = srcy - (float)i0;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) backward_warp_kernel(BwParams p) {
                 gl = lx + (-is) * p.delta_scale;
                 gr = lx + is * p.delta_scale;
             } else {
-                float srcx = p.sx * (float)x;
+                float srcx = __fmul_rn(p.sx, (float)x);
                 int j0 = min((int)srcx, p.w - 1);
                 int j1 = min(j0 + 1, p.w - 1);
                 float lx1 = srcx - (float)j0, lx0 = 1.f - lx1;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) backward_warp_row_kernel(BwParams p, int 
     int i0 = y, i1 = y;
     float ly1 = 0.f;
     if (!same) {
-        float srcy = p.sy * (float)y;
+        float srcy = __fmul_rn(p.sy, (float)y);   // rounded like ATen's h1r (no fma into the lambda below)
         i0 = min((int)srcy, p.h - 1);
         i1 = min(i0 + 1, p.h - 1);
         ly1 = srcy - (float)i0;
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) backward_warp_row_kernel(BwParams p, int 
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const int x = min(x0 + v, p.W - 1);
-            const float srcx = p.sx * (float)x;
+            const float srcx = __fmul_rn(p.sx, (float)x);
             const int j0 = min((int)srcx, p.w - 1);
             const float lx1 = srcx - (float)j0, lx0 = 1.f - lx1;
             const float4 t0 = *reinterpret_cast<const float4*>(gt + j0);

@@ -61,7 +61,7 @@ __device__ float aa_bilinear_sample(const float* __restrict__ src, int h, int w,
                                     int y, int X) {
     const float sup_y = scale_y >= 1.f ? scale_y : 1.f, inv_y = scale_y >= 1.f ? 1.f / scale_y : 1.f;
     const float sup_x = scale_x >= 1.f ? scale_x : 1.f, inv_x = scale_x >= 1.f ? 1.f / scale_x : 1.f;
-    const float cy = scale_y * ((float)y + 0.5f), cx = scale_x * ((float)X + 0.5f);
+    const float cy = __fmul_rn(scale_y, (float)y + 0.5f), cx = __fmul_rn(scale_x, (float)X + 0.5f);
     const int ymin = max((int)(cy - sup_y + 0.5f), 0);
     const int ysize = min((int)(cy + sup_y + 0.5f), h) - ymin;
     const int xmin = max((int)(cx - sup_x + 0.5f), 0);
@@ -87,7 +87,7 @@ __device__ float aa_bilinear_sample(const float* __restrict__ src, int h, int w,
 __global__ void depth_coltab_kernel(float4* __restrict__ tab, int W, int w, float scale_x) {
     const int X = blockIdx.x * blockDim.x + threadIdx.x;
     if (X >= W) return;
-    const float cx = scale_x * ((float)X + 0.5f);
+    const float cx = __fmul_rn(scale_x, (float)X + 0.5f);
     const int xmin = max((int)(cx - 1.0f + 0.5f), 0);
     const int xsize = min((int)(cx + 1.0f + 0.5f), w) - xmin;
     float wv[3] = {0.f, 0.f, 0.f}, tx = 0.f;
@@ -98,7 +98,7 @@ __global__ void depth_coltab_kernel(float4* __restrict__ tab, int W, int w, floa
 // same arithmetic as aa_bilinear_sample for the upsampling case, with the horizontal taps taken from the table
 __device__ __forceinline__ float aa_bilinear_sample_tab(const float* __restrict__ src, int h, int w, float scale_y, int y,
                                                         const float4 ct) {
-    const float cy = scale_y * ((float)y + 0.5f);
+    const float cy = __fmul_rn(scale_y, (float)y + 0.5f);
     const int ymin = max((int)(cy - 1.0f + 0.5f), 0);
     const int ysize = min((int)(cy + 1.0f + 0.5f), h) - ymin;
     const int xmin = __float_as_int(ct.x);

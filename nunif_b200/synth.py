@@ -193,3 +193,65 @@ def synth_depth(seed, b, h, w, boxes=True):
     mn = d.amin(dim=(1, 2, 3), keepdim=True)
     mx = d.amax(dim=(1, 2, 3), keepdim=True)
     return ((d - mn) / (mx - mn)).contiguous()
+
+
+def depth_anything_v2_state_dict(seed=0, encoder="vits", pos_grid=37):
+    """Seeded Depth-Anything-V2 weights with the upstream key names (`pretrained.*` = DINOv2 ViT, `depth_head.*` = DPT head).
+    No checkpoint can be downloaded here; gains are chosen so that activations stay O(1) through the 12 blocks and the
+    predicted depth is a non-trivial positive map.  pos_grid=37 is the 518/14 training grid of the released models."""
+    dim, depth, heads, feat, oc = {"vits": (384, 12, 6, 64, (48, 96, 192, 384)),
+                                   "vitb": (768, 12, 12, 128, (96, 192, 384, 768))}[encoder]
+    g = torch.Generator().manual_seed(10_000 + seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    sd = {}
+    sd["pretrained.cls_token"] = rn(1, 1, dim, std=0.02)
+    sd["pretrained.pos_embed"] = rn(1, 1 + pos_grid * pos_grid, dim, std=0.2)
+    sd["pretrained.mask_token"] = torch.zeros(1, dim)
+    sd["pretrained.patch_embed.proj.weight"] = rn(dim, 3, 14, 14, std=1.0 / (3 * 14 * 14) ** 0.5)
+    sd["pretrained.patch_embed.proj.bias"] = rn(dim, std=0.02)
+    for i in range(depth):
+        p = f"pretrained.blocks.{i}."
+        sd[p + "norm1.weight"] = 1.0 + rn(dim, std=0.1)
+        sd[p + "norm1.bias"] = rn(dim, std=0.05)
+        sd[p + "attn.qkv.weight"] = rn(3 * dim, dim, std=1.2 / dim ** 0.5)
+        sd[p + "attn.qkv.bias"] = rn(3 * dim, std=0.02)
+        sd[p + "attn.proj.weight"] = rn(dim, dim, std=1.0 / dim ** 0.5)
+        sd[p + "attn.proj.bias"] = rn(dim, std=0.02)
+        sd[p + "ls1.gamma"] = 0.3 + rn(dim, std=0.05)
+        sd[p + "norm2.weight"] = 1.0 + rn(dim, std=0.1)
+        sd[p + "norm2.bias"] = rn(dim, std=0.05)
+        sd[p + "mlp.fc1.weight"] = rn(4 * dim, dim, std=1.0 / dim ** 0.5)
+        sd[p + "mlp.fc1.bias"] = rn(4 * dim, std=0.02)
+        sd[p + "mlp.fc2.weight"] = rn(dim, 4 * dim, std=1.0 / (4 * dim) ** 0.5)
+        sd[p + "mlp.fc2.bias"] = rn(dim, std=0.02)
+        sd[p + "ls2.gamma"] = 0.3 + rn(dim, std=0.05)
+    sd["pretrained.norm.weight"] = 1.0 + rn(dim, std=0.1)
+    sd["pretrained.norm.bias"] = rn(dim, std=0.05)
+    for i, c in enumerate(oc):
+        sd[f"depth_head.projects.{i}.weight"] = rn(c, dim, 1, 1, std=1.0 / dim ** 0.5)
+        sd[f"depth_head.projects.{i}.bias"] = rn(c, std=0.02)
+        sd[f"depth_head.scratch.layer{i + 1}_rn.weight"] = rn(feat, c, 3, 3, std=1.0 / (9 * c) ** 0.5)
+    sd["depth_head.resize_layers.0.weight"] = rn(oc[0], oc[0], 4, 4, std=1.0 / oc[0] ** 0.5)
+    sd["depth_head.resize_layers.0.bias"] = rn(oc[0], std=0.02)
+    sd["depth_head.resize_layers.1.weight"] = rn(oc[1], oc[1], 2, 2, std=1.0 / oc[1] ** 0.5)
+    sd["depth_head.resize_layers.1.bias"] = rn(oc[1], std=0.02)
+    sd["depth_head.resize_layers.3.weight"] = rn(oc[3], oc[3], 3, 3, std=1.0 / (9 * oc[3]) ** 0.5)
+    sd["depth_head.resize_layers.3.bias"] = rn(oc[3], std=0.02)
+    for r in (1, 2, 3, 4):
+        p = f"depth_head.scratch.refinenet{r}."
+        sd[p + "out_conv.weight"] = rn(feat, feat, 1, 1, std=1.0 / feat ** 0.5)
+        sd[p + "out_conv.bias"] = rn(feat, std=0.02)
+        for u in (1, 2):
+            for cv in (1, 2):
+                sd[p + f"resConfUnit{u}.conv{cv}.weight"] = rn(feat, feat, 3, 3, std=0.7 / (9 * feat) ** 0.5)
+                sd[p + f"resConfUnit{u}.conv{cv}.bias"] = rn(feat, std=0.02)
+    sd["depth_head.scratch.output_conv1.weight"] = rn(feat // 2, feat, 3, 3, std=1.0 / (9 * feat) ** 0.5)
+    sd["depth_head.scratch.output_conv1.bias"] = rn(feat // 2, std=0.02)
+    sd["depth_head.scratch.output_conv2.0.weight"] = rn(32, feat // 2, 3, 3, std=1.4 / (9 * feat // 2) ** 0.5)
+    sd["depth_head.scratch.output_conv2.0.bias"] = 0.2 + rn(32, std=0.05)
+    sd["depth_head.scratch.output_conv2.2.weight"] = rn(1, 32, 1, 1, std=1.0 / 32 ** 0.5).abs()
+    sd["depth_head.scratch.output_conv2.2.bias"] = torch.full((1,), 0.3)
+    return sd

@@ -65,6 +65,26 @@ def test_conv3(B, H, W, Cin, N, act):
     assert err < 1e-2, err
 
 
+@pytest.mark.parametrize("B,H,W,Cin,N,act,use_res", [(2, 28, 49, 64, 64, 3, False), (1, 14, 25, 384, 64, 0, False), (2, 56, 98, 96, 64, 0, True),
+                                                       (3, 9, 7, 32, 32, 3, False), (1, 112, 196, 64, 32, 0, True), (2, 5, 3, 192, 64, 0, False)])
+def test_conv3_same_padding(B, H, W, Cin, N, act, use_res):
+    """kind 4: 3x3 conv with zero padding 1 - the halo is the tensor map's out-of-bounds zero fill (DPT head convs)."""
+    g = torch.Generator(device="cpu").manual_seed(H * W + Cin + 1)
+    A = torch.randn(B, H, W, Cin, generator=g).half().to(DEV)
+    Wc = (torch.randn(N, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).half().to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(B, H, W, N, generator=g).half().to(DEV) if use_res else None
+    Wt = Wc.permute(0, 2, 3, 1).reshape(N, 9 * Cin).contiguous()
+    out = torch.full((B, H, W, N), 7.0, dtype=torch.float16, device=DEV)
+    run(A, 4, Wt, b, act, out, res=res)
+    ref = act_ref(F.conv2d(A.permute(0, 3, 1, 2).float(), Wc.float(), b, padding=1), act).permute(0, 2, 3, 1)
+    if use_res:
+        ref = ref.half().float() + res.float()
+    err = (out.float() - ref).abs().max().item()
+    log_metric("gemm_conv3_same", H=H, W=W, Cin=Cin, N=N, err=err)
+    assert err < 1e-2, err
+
+
 @pytest.mark.parametrize("B,H,C,N", [(2, 24, 96, 192), (1, 36, 192, 192), (2, 20, 64, 64), (1, 12, 128, 128)])
 def test_down2(B, H, C, N):
     g = torch.Generator(device="cpu").manual_seed(H + C)

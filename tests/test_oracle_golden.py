@@ -204,3 +204,70 @@ def test_da_preprocess_oracle_matches_reference():
     assert np.abs(ofr.batch_preprocess(g["x"], lower_bound=126) - g["prep_126"]).max() < 3e-6
     assert np.abs(ofr.batch_preprocess(g["x"], lower_bound=392, limit_resolution=True) - g["prep_98_limit"]).max() < 3e-6
     assert np.abs(ofr.batch_preprocess(g["xt"], lower_bound=70) - g["prep_tall"]).max() < 3e-6
+
+
+def _da_to_hf(sd, depth=12):
+    """oracle (upstream Depth-Anything-V2 key names) -> transformers.DepthAnythingForDepthEstimation key names."""
+    out = {}
+    out["backbone.embeddings.cls_token"] = sd["pretrained.cls_token"]
+    out["backbone.embeddings.mask_token"] = sd["pretrained.mask_token"]
+    out["backbone.embeddings.position_embeddings"] = sd["pretrained.pos_embed"]
+    out["backbone.embeddings.patch_embeddings.projection.weight"] = sd["pretrained.patch_embed.proj.weight"]
+    out["backbone.embeddings.patch_embeddings.projection.bias"] = sd["pretrained.patch_embed.proj.bias"]
+    for i in range(depth):
+        p, q = f"pretrained.blocks.{i}.", f"backbone.encoder.layer.{i}."
+        dim = sd[p + "norm1.weight"].shape[0]
+        for n in ("norm1", "norm2"):
+            out[q + n + ".weight"], out[q + n + ".bias"] = sd[p + n + ".weight"], sd[p + n + ".bias"]
+        w, b = sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]
+        for j, n in enumerate(("query", "key", "value")):
+            out[q + f"attention.attention.{n}.weight"] = w[j * dim:(j + 1) * dim]
+            out[q + f"attention.attention.{n}.bias"] = b[j * dim:(j + 1) * dim]
+        out[q + "attention.output.dense.weight"], out[q + "attention.output.dense.bias"] = sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]
+        out[q + "layer_scale1.lambda1"], out[q + "layer_scale2.lambda1"] = sd[p + "ls1.gamma"], sd[p + "ls2.gamma"]
+        for n in ("fc1", "fc2"):
+            out[q + f"mlp.{n}.weight"], out[q + f"mlp.{n}.bias"] = sd[p + f"mlp.{n}.weight"], sd[p + f"mlp.{n}.bias"]
+    out["backbone.layernorm.weight"], out["backbone.layernorm.bias"] = sd["pretrained.norm.weight"], sd["pretrained.norm.bias"]
+    for i in range(4):
+        out[f"neck.reassemble_stage.layers.{i}.projection.weight"] = sd[f"depth_head.projects.{i}.weight"]
+        out[f"neck.reassemble_stage.layers.{i}.projection.bias"] = sd[f"depth_head.projects.{i}.bias"]
+        if i != 2:
+            out[f"neck.reassemble_stage.layers.{i}.resize.weight"] = sd[f"depth_head.resize_layers.{i}.weight"]
+            out[f"neck.reassemble_stage.layers.{i}.resize.bias"] = sd[f"depth_head.resize_layers.{i}.bias"]
+        out[f"neck.convs.{i}.weight"] = sd[f"depth_head.scratch.layer{i + 1}_rn.weight"]
+        p, q = f"depth_head.scratch.refinenet{4 - i}.", f"neck.fusion_stage.layers.{i}."
+        out[q + "projection.weight"], out[q + "projection.bias"] = sd[p + "out_conv.weight"], sd[p + "out_conv.bias"]
+        for u in (1, 2):
+            for cv in (1, 2):
+                for wb in ("weight", "bias"):
+                    out[q + f"residual_layer{u}.convolution{cv}.{wb}"] = sd[p + f"resConfUnit{u}.conv{cv}.{wb}"]
+    s = "depth_head.scratch."
+    for hf, up in (("conv1", "output_conv1"), ("conv2", "output_conv2.0"), ("conv3", "output_conv2.2")):
+        out[f"head.{hf}.weight"], out[f"head.{hf}.bias"] = sd[s + up + ".weight"], sd[s + up + ".bias"]
+    return out
+
+
+def test_depth_anything_oracle_matches_transformers():
+    """The Depth-Anything-V2 network is third-party code absent from /root/reference (torch.hub).  Pin the oracle's
+    restatement against the independent public implementation in this image (transformers), same weights."""
+    transformers = pytest.importorskip("transformers")
+    from transformers import DepthAnythingConfig, DepthAnythingForDepthEstimation, Dinov2Config
+    from oracle import depth_anything as oda
+    grid = 6
+    sd = synth.depth_anything_v2_state_dict(3, pos_grid=grid)
+    cfg = DepthAnythingConfig(
+        backbone_config=Dinov2Config(hidden_size=384, num_hidden_layers=12, num_attention_heads=6, mlp_ratio=4, image_size=14 * grid,
+                                     patch_size=14, out_features=["stage3", "stage6", "stage9", "stage12"],
+                                     reshape_hidden_states=False, apply_layernorm=True, layer_norm_eps=1e-6),
+        reassemble_hidden_size=384, neck_hidden_sizes=[48, 96, 192, 384], fusion_hidden_size=64, head_hidden_size=32,
+        patch_size=14, reassemble_factors=[4, 2, 1, 0.5])
+    hf = DepthAnythingForDepthEstimation(cfg).eval()
+    missing, unexpected = hf.load_state_dict(_da_to_hf(sd), strict=False)
+    assert not unexpected and all("position_ids" in m or "rel" in m for m in missing), (missing, unexpected)
+    x = torch.randn(2, 3, 14 * grid, 14 * grid, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = hf(pixel_values=x).predicted_depth
+        got = oda.depth_anything_forward(sd, x)
+    assert got.shape == want.shape == (2, 14 * grid, 14 * grid)
+    assert float(want.std()) > 0.1
+    assert float((got - want).abs().max()) < 2e-4 * float(want.abs().max())
