@@ -166,7 +166,37 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
                        "warp_kernel_ms": k["ms"], "warp_kernel_GBps_algorithmic": gbs, "warp_frac_of_hbm_peak": gbs / peaks_gbs,
                        "kernel_classes_ms": {kk: round(v["ms"], 4) for kk, v in prof.items()}}
         del y
-    out["note"] = "post-depth stages only (dilate_edge [2,1], minmax, warp, SBS); depth network not included"
+    out["note"] = "forward_fill / backward: post-depth stages only (dilate_edge [2,1], minmax, warp, SBS) on a synthetic depth map"
+    # ---- the whole per-frame path of BASELINE configs[2]: Depth-Anything-V2-S (seeded weights) at resolution 392 +
+    # dilate_edge [2,1] + min/max + forward_fill warp + SBS, frames resident in HBM as float CHW
+    from nunif_b200.iw3 import DepthAnythingModel
+    dam = DepthAnythingModel().load_state_dict(synth.depth_anything_v2_state_dict(0), gpu=dev.index or 0)
+
+    def full(method):
+        with torch.inference_mode():
+            depth = dam.infer(c, edge_dilation=[2, 1])
+            return stereo_sbs(c, depth, 2.0, 0.5, method=method, edge_dilation=0)
+    for method in ("forward_fill", "backward"):
+        for _ in range(3):
+            y = full(method)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            y = full(method)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        _lib.check(lib.nb200_profile_enable(1))
+        y = full(method)
+        buf = ctypes.create_string_buffer(8192)
+        _lib.check(lib.nb200_profile_report(buf, 8192))
+        _lib.check(lib.nb200_profile_enable(0))
+        prof = json.loads(buf.value.decode())
+        out["with_depth_" + method] = {"fps": B / (ms / 1e3), "ms_per_batch": ms, "batch": B,
+                                       "depth_model": "Depth-Anything-V2 ViT-S (seeded random weights), 392x686 network input",
+                                       "kernel_classes_ms": {kk: round(v["ms"], 4) for kk, v in prof.items()}}
+        del y
     return out
 
 

@@ -62,7 +62,9 @@ def test_depth_anything_1080p_infer_pipeline():
         assert torch.equal(d1, dilate_edge(d[:1], 2)[0])
         dt = model.infer(x.to(DEV), tta=True)
         flipped = model.infer(torch.flip(x, dims=[3]).to(DEV))
-        assert stats(dt, (d + torch.flip(flipped, dims=[3])) * 0.5)["max"] < 1e-6 * float(d.abs().max()) + 1e-6
+        # the network output is fp16-quantised (reference numerics) and the GEMM tiling depends on the batch size:
+        # allow two fp16 ulps at the top of the range
+        assert stats(dt, (d + torch.flip(flipped, dims=[3])) * 0.5)["max"] <= 2 ** -9 * float(d.abs().max())
 
 
 def test_pos_table_interpolation_matches_oracle():
