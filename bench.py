@@ -197,7 +197,66 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
                                        "depth_model": "Depth-Anything-V2 ViT-S (seeded random weights), 392x686 network input",
                                        "kernel_classes_ms": {kk: round(v["ms"], 4) for kk, v in prof.items()}}
         del y
+    # ---- the same path end to end from HOST uint8 frames (video.py to_tensor / from_tensor edges): pinned uint8 HWC in,
+    # H2D, uint8->float CHW, depth, warp, SBS, float->uint8 HWC, D2H of the SBS frames
+    from nunif_b200.iw3 import hwc_to_chw_float, chw_float_to_hwc
+    u8_in = (c.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).cpu().pin_memory()
+    u8_out = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8).pin_memory()
+
+    def e2e():
+        with torch.inference_mode():
+            xf = hwc_to_chw_float(u8_in.to(dev, non_blocking=True))
+            depth = dam.infer(xf, edge_dilation=[2, 1])
+            sbs = stereo_sbs(xf, depth, 2.0, 0.5, method="forward_fill", edge_dilation=0)
+            u8_out.copy_(chw_float_to_hwc(sbs), non_blocking=True)
+    for _ in range(3):
+        e2e()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out["e2e_uint8_host_forward_fill"] = {"fps": B / (ms / 1e3), "ms_per_batch": ms, "batch": B,
+                                          "h2d_bytes_per_batch": int(u8_in.numel()), "d2h_bytes_per_batch": int(u8_out.numel())}
     return out
+
+
+def bench_upcunet(dev, lib, x, iters=3):
+    """Secondary: the 2x model of BASELINE configs[0] (UpCUNet, cunet/art noise1_scale2x layout, seeded weights) on the same
+    4K frame, tile 256, batch 16 (180 tiles, 81.9 GFLOP each): device-timed, frame resident in HBM."""
+    import ctypes
+    import torch
+    from nunif_b200 import synth, _lib
+    from nunif_b200.nunif.models import create_model
+    from nunif_b200.nunif.render import tiled_render
+    m = create_model("waifu2x.upcunet", synth.upcunet_state_dict(0), dev)
+    with torch.no_grad():
+        for _ in range(2):
+            y = tiled_render(x, m, tile_size=TILE, batch_size=BATCH)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            y = tiled_render(x, m, tile_size=TILE, batch_size=BATCH)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        _lib.check(lib.nb200_profile_enable(1))
+        y = tiled_render(x, m, tile_size=TILE, batch_size=BATCH)
+        buf = ctypes.create_string_buffer(8192)
+        _lib.check(lib.nb200_profile_report(buf, 8192))
+        _lib.check(lib.nb200_profile_enable(0))
+        prof = json.loads(buf.value.decode())
+        del y
+    h, w = x.shape[1], x.shape[2]
+    gemm = prof.get("gemm", {"ms": 0.0, "work": 0.0})
+    return {"ms_per_frame": ms, "input_megapixels_per_sec": h * w / 1e6 / (ms / 1e3), "tiles": 180,
+            "model_tflops_per_sec": 180 * 81.9 / 1e3 / (ms / 1e3),
+            "gemm_tflops_per_sec": gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] else None,
+            "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
 
 
 def run_b200(args):
@@ -289,6 +348,7 @@ def run_b200(args):
         del y
 
         iw3 = bench_iw3(dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if rank == 0 else None
+        upc = bench_upcunet(dev, lib, x) if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -341,6 +401,8 @@ def run_b200(args):
                                "share_of_step": attn["ms"] / total_prof_ms if total_prof_ms else None},
         "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }
+    if upc is not None:
+        line["upcunet_4k_2x"] = upc
     if iw3 is not None:
         line["iw3_1080p"] = iw3
     if rank == 0:
