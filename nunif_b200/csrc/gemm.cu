@@ -85,7 +85,7 @@ constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*bar
 unsigned long long* g_timeline = nullptr;
 int g_tune[8] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, /*3 force gather backward warp*/ 0,
                  /*4 forced BLOCK_N*/ 0, /*5 disable GELU->128 rule*/ 0,
-                 /*6 attention smem carveout %*/ 0, 0};
+                 /*6 attention smem carveout %*/ 0, /*7 SIMT tail convs*/ 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {

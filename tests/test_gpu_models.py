@@ -54,6 +54,25 @@ def test_cunet_forward(name, up):
 
 
 @pytest.mark.parametrize("name,up", [("upcunet", True), ("cunet", False)])
+def test_cunet_tail_tensor_core_and_simt_kernels_agree(name, up):
+    """The 3-channel tail convs run on mma.sync (fp16 weights, as the reference under autocast); the SIMT kernel
+    (fp32 weights) is the fallback.  Both must give the same tile up to that weight rounding."""
+    from nunif_b200 import _lib
+    from nunif_b200.nunif.models import create_model
+    g = load_golden(name)
+    sd = synth.upcunet_state_dict(0) if up else synth.cunet_state_dict(0)
+    m = create_model("waifu2x." + name, sd, DEV)
+    x = t(g["x"], DEV)
+    a = m(x).float()
+    _lib.lib().nb200_tune_set(7, 1)
+    try:
+        b = m(x).float()
+    finally:
+        _lib.lib().nb200_tune_set(7, 0)
+    assert stats(a, b)["max"] < 2e-3, stats(a, b)
+
+
+@pytest.mark.parametrize("name,up", [("upcunet", True), ("cunet", False)])
 def test_cunet_tiled_render(name, up):
     from nunif_b200.nunif.models import create_model
     from nunif_b200.nunif.render import tiled_render
