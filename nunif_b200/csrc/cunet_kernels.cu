@@ -203,75 +203,85 @@ __global__ void __launch_bounds__(128) tail_conv_kernel(const __half* __restrict
     }
 }
 
-// Tensor-core version of the tails (production path): the 3 output channels are padded to the n=8 of
-// mma.sync.m16n8k16; a warp owns 16 output pixels of one image row (for the ConvTranspose: 16 pixels of one column
-// parity, so that all rows of the MMA share the same 2x2 subset of the 4x4 taps), A fragments are gathered straight
-// from the NHWC fp16 activation (implicit im2col, 4-byte loads that hit L1), B fragments come from a shared-memory copy
-// of the weights in fp16 (the reference runs these convs in fp16 under autocast as well).
-// 16 instructions per output pixel instead of ~3500 for the SIMT kernel above (kept as the fallback / cross-check).
+// Tensor-core version of the tails (production path).  The 3 output channels are padded to the n=8 of
+// mma.sync.m16n8k16; a warp owns 16 output pixels (for the ConvTranspose: 16 pixels of one column parity, so that all
+// rows of the MMA share the same 2x2 subset of the 4x4 taps).  The block first stages its input window in shared memory
+// (zero-filled outside the image; pixel stride 144 B so that fragment loads are bank-conflict free) - without that every
+// tap re-reads its 128-byte pixel from L2 and the kernel is L2-bandwidth bound (0.8 ms per launch; same for the SIMT
+// kernel above, kept as fallback / cross-check).  Weights are staged as fp16 B fragments (the reference runs these convs
+// in fp16 under autocast as well).
+//   MODE 0 (conv 3x3):        block = 2 output rows x 64 columns, window 4 x 66 pixels
+//   MODE 1 (ConvT 4x4 s2 p3): block = 1 output row x 128 columns (64 per parity), window 2 x 66 pixels
+constexpr int TC_PS = 72;        // halves per staged pixel (64 channels + 8 pad)
+constexpr int TC_WC = 66;        // staged window columns
 template <int MODE, int EPI>
-__global__ void __launch_bounds__(128) tail_conv_mma_kernel(const __half* __restrict__ x, const float* __restrict__ wt,
+__global__ void __launch_bounds__(256) tail_conv_mma_kernel(const __half* __restrict__ x, const float* __restrict__ wt,
                                                             const float* __restrict__ bias, __half* __restrict__ out,
                                                             const __half* __restrict__ z1, int Hi, int Wi, int Ho, int Wo,
                                                             int z1H, int z1W, int clip) {
     constexpr int TAPS = MODE == 0 ? 9 : 16;
-    // sB[tap][kc (4 chunks of 16 channels)][n (8)][16 halves]; rows n >= 3 are zero
-    __shared__ __align__(16) __half sB[TAPS * 4 * 8 * 16];
-    for (int i = threadIdx.x; i < TAPS * 4 * 8 * 16; i += blockDim.x) {
+    constexpr int WR = MODE == 0 ? 4 : 2;                        // staged window rows
+    extern __shared__ __align__(16) unsigned char tc_smem[];
+    __half* sB = reinterpret_cast<__half*>(tc_smem);             // [tap][kc][n (8)][16 halves]; rows n >= 3 are zero
+    __half* sX = sB + TAPS * 512;                                // [WR][66][72]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.z;
+    // block origin in output and input space
+    const int j0 = blockIdx.x * 64;                              // first output column (MODE 1: first index within a parity)
+    const int oy0 = MODE == 0 ? blockIdx.y * 2 : blockIdx.y;
+    int iy0, ix0;
+    if (MODE == 0) { iy0 = oy0; ix0 = j0; }
+    else {
+        // oy = 2*iy - 3 + ky: the two rows that feed output row oy are iy_lo, iy_lo + 1 with iy_lo = (oy + 3 - ky_hi) / 2
+        const int ky_hi = ((oy0 + 3) & 1) + 2;
+        iy0 = (oy0 + 3 - ky_hi) >> 1;                            // may be -1 at the top edge (zero-filled)
+        ix0 = j0;                                                // columns j0 .. j0 + 65 (see tap table below)
+    }
+    for (int i = tid; i < TAPS * 512; i += 256) {
         const int k = i & 15, nn = (i >> 4) & 7, kc = (i >> 7) & 3, t = i >> 9;
         sB[i] = __float2half_rn(nn < 3 ? wt[(t * 64 + kc * 16 + k) * 3 + nn] : 0.f);
     }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-    const int oy = blockIdx.y % Ho, b = blockIdx.y / Ho;
-    const int par = MODE == 1 ? blockIdx.z : 0;                  // column parity class of the ConvTranspose
-    const int j0 = (blockIdx.x * 4 + warp) * 16;                 // first pixel (index within the parity class) of this warp
-    const int npx = MODE == 1 ? Wo / 2 : Wo;
-    if (j0 >= npx) return;
-    const int jr[2] = {j0 + g, j0 + g + 8};                      // the two accumulator rows of this thread
-    int ox[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) ox[r] = MODE == 1 ? 2 * min(jr[r], npx - 1) + par : min(jr[r], npx - 1);
     const __half* xb = x + (size_t)b * Hi * Wi * 64;
+    for (int i = tid; i < WR * TC_WC * 8; i += 256) {
+        const int c8 = i & 7, col = (i >> 3) % TC_WC, r = (i >> 3) / TC_WC;
+        const int iy = iy0 + r, ix = ix0 + col;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)iy * Wi + ix) * 64) + c8);
+        *reinterpret_cast<uint4*>(sX + (r * TC_WC + col) * TC_PS + c8 * 8) = v;
+    }
+    __syncthreads();
+    // this warp's 16 pixels
+    const int lrow = MODE == 0 ? warp >> 2 : 0;                  // local output row
+    const int par = MODE == 1 ? warp >> 2 : 0;                   // column parity class
+    const int lj = (warp & 3) * 16;                              // first local column index
+    const int oy = oy0 + lrow;
+    const int npx = MODE == 1 ? Wo / 2 : Wo;
+    if (oy >= Ho || j0 + lj >= npx) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int NT = MODE == 0 ? 9 : 4;
 #pragma unroll 1
     for (int tt = 0; tt < NT; ++tt) {
-        int tap, iy, ix[2];
-        bool ok[2];
-        if (MODE == 0) {
-            tap = tt;
-            iy = oy + tt / 3;
-            ix[0] = ox[0] + tt % 3; ix[1] = ox[1] + tt % 3;
-            ok[0] = ok[1] = true;
-        } else {
-            // oy = 2*iy - 3 + ky  =>  ky has the parity of oy+3; same for x (cunet.py:41 ConvTranspose2d(64, 3, 4, 2, 3))
+        int tap, dr, dc;
+        if (MODE == 0) { tap = tt; dr = lrow + tt / 3; dc = tt % 3; }
+        else {
+            // ky has the parity of oy+3, kx that of ox+3 (cunet.py:41 ConvTranspose2d(64, 3, 4, 2, 3));
+            // ix = (2j + par + 3 - kx) / 2 = j + (par + 3 - kx) / 2
             const int ky = ((oy + 3) & 1) + 2 * (tt >> 1), kx = ((par + 3) & 1) + 2 * (tt & 1);
             tap = ky * 4 + kx;
-            iy = (oy + 3 - ky) >> 1;
-            const bool yok = iy >= 0 && iy < Hi;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                ix[r] = (ox[r] + 3 - kx) >> 1;
-                ok[r] = yok && ix[r] >= 0 && ix[r] < Wi;
-            }
-            iy = min(max(iy, 0), Hi - 1);
+            dr = ((oy + 3 - ky) >> 1) - iy0;
+            dc = (par + 3 - kx) >> 1;
         }
-        const __half* p0 = xb + ((size_t)iy * Wi + min(max(ix[0], 0), Wi - 1)) * 64 + 2 * t4;
-        const __half* p1 = xb + ((size_t)iy * Wi + min(max(ix[1], 0), Wi - 1)) * 64 + 2 * t4;
-        const __half* wb = sB + (size_t)tap * 512 + g * 16 + 2 * t4;
+        const __half* p0 = sX + (dr * TC_WC + lj + g + dc) * TC_PS + 2 * t4;
+        const __half* p1 = p0 + 8 * TC_PS;
+        const __half* wb = sB + tap * 512 + g * 16 + 2 * t4;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
-            uint32_t a[4];
-            a[0] = ok[0] ? __ldg(reinterpret_cast<const uint32_t*>(p0 + kc * 16)) : 0u;
-            a[1] = ok[1] ? __ldg(reinterpret_cast<const uint32_t*>(p1 + kc * 16)) : 0u;
-            a[2] = ok[0] ? __ldg(reinterpret_cast<const uint32_t*>(p0 + kc * 16 + 8)) : 0u;
-            a[3] = ok[1] ? __ldg(reinterpret_cast<const uint32_t*>(p1 + kc * 16 + 8)) : 0u;
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wb + kc * 128);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wb + kc * 128 + 8);
+            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(p0 + kc * 16), a1 = *reinterpret_cast<const uint32_t*>(p1 + kc * 16);
+            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(p0 + kc * 16 + 8), a3 = *reinterpret_cast<const uint32_t*>(p1 + kc * 16 + 8);
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wb + kc * 128), b1 = *reinterpret_cast<const uint32_t*>(wb + kc * 128 + 8);
             asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                          : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
-                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
         }
     }
     // accumulator layout: acc[0..1] = row g, channels 2*t4, 2*t4+1; acc[2..3] = row g+8.  Channels 0,1 live in t4 == 0,
@@ -281,9 +291,11 @@ __global__ void __launch_bounds__(128) tail_conv_mma_kernel(const __half* __rest
     const float bv[3] = {bias[0], bias[1], bias[2]};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        if (jr[r] >= npx) continue;
+        const int j = j0 + lj + g + 8 * r;
+        if (j >= npx) continue;
+        const int ox = MODE == 1 ? 2 * j + par : j;
         float v[3] = {(r ? acc[2] : acc[0]) + bv[0], (r ? acc[3] : acc[1]) + bv[1], (r ? c2b : c2a) + bv[2]};
-        const size_t pix = ((size_t)b * Ho + oy) * Wo + ox[r];
+        const size_t pix = ((size_t)b * Ho + oy) * Wo + ox;
         if (EPI == 0) {
             __align__(16) __half o[8];
 #pragma unroll
@@ -292,12 +304,28 @@ __global__ void __launch_bounds__(128) tail_conv_mma_kernel(const __half* __rest
             for (int k = 3; k < 8; ++k) o[k] = __float2half_rn(0.f);
             reinterpret_cast<uint4*>(out)[pix] = *reinterpret_cast<const uint4*>(o);
         } else {
-            const __half* zp = z1 + (((size_t)b * z1H + oy + 20) * z1W + ox[r] + 20) * 8;
+            const __half* zp = z1 + (((size_t)b * z1H + oy + 20) * z1W + ox + 20) * 8;
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-                out[(((size_t)b * 3 + k) * Ho + oy) * Wo + ox[r]] = __float2half_rn(clamp01(v[k] + __half2float(zp[k])));
+                out[(((size_t)b * 3 + k) * Ho + oy) * Wo + ox] = __float2half_rn(clamp01(v[k] + __half2float(zp[k])));
         }
     }
+}
+
+template <int MODE, int EPI>
+static int launch_tail_mma(cudaStream_t st, const __half* x, const float* wt, const float* bias, __half* out, const __half* z1, int n,
+                           int Hi, int Wi, int Ho, int Wo, int z1H, int z1W, int clip) {
+    constexpr int TAPS = MODE == 0 ? 9 : 16, WR = MODE == 0 ? 4 : 2;
+    const size_t smem = (size_t)(TAPS * 512 + WR * TC_WC * TC_PS) * sizeof(__half);
+    static bool cfg = false;
+    if (!cfg) {
+        NB_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = true;
+    }
+    const int npx = MODE == 1 ? Wo / 2 : Wo;
+    const dim3 grid(cdiv(npx, 64), MODE == 0 ? cdiv(Ho, 2) : Ho, n);
+    tail_conv_mma_kernel<MODE, EPI><<<grid, 256, smem, st>>>(x, wt, bias, out, z1, Hi, Wi, Ho, Wo, z1H, z1W, clip);
+    return 0;
 }
 
 extern int g_tune[8];  // gemm.cu; [7] != 0 selects the SIMT tail kernel (tests)
@@ -308,13 +336,13 @@ int tail_conv(cudaStream_t st, int mode, int epi, const __half* x, const float* 
     const size_t total = (size_t)n * Ho * Wo;
     const unsigned blocks = (unsigned)cdiv64(total, 128);
     ProfScope ps(st, PC_TAIL, (double)n * Hi * Wi * 128 + (double)total * 16);
-    if (g_tune[7] == 0 && (mode == 0 || Wo % 2 == 0)) {
-        const int npx = mode == 1 ? Wo / 2 : Wo;
-        const dim3 grid(cdiv(npx, 64), (unsigned)(n * Ho), mode == 1 ? 2 : 1);
-        if (mode == 0 && epi == 0) tail_conv_mma_kernel<0, 0><<<grid, 128, 0, st>>>(x, wt, bias, out, z1, Hi, Wi, Ho, Wo, z1H, z1W, clip);
-        else if (mode == 0 && epi == 1) tail_conv_mma_kernel<0, 1><<<grid, 128, 0, st>>>(x, wt, bias, out, z1, Hi, Wi, Ho, Wo, z1H, z1W, clip);
-        else if (mode == 1 && epi == 0) tail_conv_mma_kernel<1, 0><<<grid, 128, 0, st>>>(x, wt, bias, out, z1, Hi, Wi, Ho, Wo, z1H, z1W, clip);
+    if (g_tune[7] == 0 && (mode == 0 || Wo % 2 == 0) && n <= 65535) {
+        int rc;
+        if (mode == 0 && epi == 0) rc = launch_tail_mma<0, 0>(st, x, wt, bias, out, z1, n, Hi, Wi, Ho, Wo, z1H, z1W, clip);
+        else if (mode == 0 && epi == 1) rc = launch_tail_mma<0, 1>(st, x, wt, bias, out, z1, n, Hi, Wi, Ho, Wo, z1H, z1W, clip);
+        else if (mode == 1 && epi == 0) rc = launch_tail_mma<1, 0>(st, x, wt, bias, out, z1, n, Hi, Wi, Ho, Wo, z1H, z1W, clip);
         else return fail("tail_conv: unsupported mode");
+        if (rc) return rc;
         NB_LAUNCHED();
         return 0;
     }
