@@ -197,6 +197,25 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
                                        "depth_model": "Depth-Anything-V2 ViT-S (seeded random weights), 392x686 network input",
                                        "kernel_classes_ms": {kk: round(v["ms"], 4) for kk, v in prof.items()}}
         del y
+    # ---- BASELINE configs[4] warp stage: 4K frame, grid_sample warp with the fused dubois anaglyph epilogue
+    c4k = torch.stack([synth.synth_image(90 + i, 3, 2160, 3840, smooth=False) for i in range(2)]).to(dev)
+    d4k = synth.synth_depth(61, 2, 384, 704).to(dev)
+
+    def ana():
+        return stereo_sbs(c4k, d4k, 2.0, 0.5, method="backward", mapper="div_6", edge_dilation=[2, 1], anaglyph="dubois")
+    for _ in range(3):
+        y = ana()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        y = ana()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out["backward_dubois_4k"] = {"fps": 2 / (ms / 1e3), "ms_per_batch": ms, "batch": 2,
+                                 "note": "post-depth stages of configs[4] (dilate_edge, minmax + div_6 mapper, grid_sample warp, dubois); ZoeDepth body not built"}
+    del y, c4k, d4k
     # ---- the same path end to end from HOST uint8 frames (video.py to_tensor / from_tensor edges): pinned uint8 HWC in,
     # H2D, uint8->float CHW, depth, warp, SBS, float->uint8 HWC, D2H of the SBS frames
     from nunif_b200.iw3 import hwc_to_chw_float, chw_float_to_hwc
@@ -222,6 +241,30 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
     out["e2e_uint8_host_forward_fill"] = {"fps": B / (ms / 1e3), "ms_per_batch": ms, "batch": B,
                                           "h2d_bytes_per_batch": int(u8_in.numel()), "d2h_bytes_per_batch": int(u8_out.numel())}
     return out
+
+
+def bench_8k_downscaled(dev, model4x, iters=2):
+    """Secondary: BASELINE configs[3] per GPU - SwinUNetDownscaled(2x) derived from the 4x weights on one 8K frame
+    (3x4320x7680, 627 tiles of 256, batch 16, 97.6 TFLOP), device-timed, frame resident in HBM."""
+    import torch
+    from nunif_b200 import synth
+    from nunif_b200.nunif.render import tiled_render
+    m2 = model4x.to_2x()
+    x8 = synth.synth_image(77, 3, 4320, 7680, smooth=False).to(dev)
+    with torch.no_grad():
+        y = tiled_render(x8, m2, tile_size=TILE, batch_size=BATCH)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            y = tiled_render(x8, m2, tile_size=TILE, batch_size=BATCH)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        shape = tuple(y.shape)
+        del y
+    return {"ms_per_frame": ms, "frames_per_sec": 1e3 / ms, "input_megapixels_per_sec": 4320 * 7680 / 1e6 / (ms / 1e3),
+            "tiles": 627, "output_shape": shape, "model_tflops_per_sec": 627 * 155.7 / 1e3 / (ms / 1e3)}
 
 
 def bench_upcunet(dev, lib, x, iters=3):
@@ -349,6 +392,7 @@ def run_b200(args):
 
         iw3 = bench_iw3(dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if rank == 0 else None
         upc = bench_upcunet(dev, lib, x) if rank == 0 else None
+        cfg4 = bench_8k_downscaled(dev, model) if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -403,6 +447,8 @@ def run_b200(args):
     }
     if upc is not None:
         line["upcunet_4k_2x"] = upc
+    if cfg4 is not None:
+        line["swin_downscaled2x_8k"] = cfg4
     if iw3 is not None:
         line["iw3_1080p"] = iw3
     if rank == 0:

@@ -68,6 +68,16 @@ static void pack_tail(Packer& pk, const std::string& name, bool deconv, size_t* 
                 const float v = deconv ? w[((size_t)ci * 3 + co) * 16 + t] : w[((size_t)co * 64 + ci) * 9 + t];
                 wv[((size_t)t * 64 + ci) * 3 + co] = __half2float(__float2half_rn(v));
             }
+    // ... followed by the same weights as fp16 mma.sync B fragments [tap][kc (4 x 16 channels)][n (8, rows >= 3 zero)][16]
+    // (tail_conv_mma_kernel copies this block to shared memory with 16-byte loads)
+    const size_t nf = wv.size();
+    wv.resize(nf + (size_t)taps * 256, 0.f);
+    __half* frag = reinterpret_cast<__half*>(wv.data() + nf);
+    for (int t = 0; t < taps; ++t)
+        for (int kc = 0; kc < 4; ++kc)
+            for (int nn = 0; nn < 8; ++nn)
+                for (int k = 0; k < 16; ++k)
+                    frag[(((size_t)t * 4 + kc) * 8 + nn) * 16 + k] = __float2half_rn(nn < 3 ? wv[((size_t)t * 64 + kc * 16 + k) * 3 + nn] : 0.f);
     *w_off = pk.add_f32(wv);
     *b_off = pk.add_f32(std::vector<float>(b, b + 3));
 }
