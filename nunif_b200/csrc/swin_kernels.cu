@@ -289,6 +289,82 @@ __global__ void __launch_bounds__(256) to_image_r4_kernel(const __half* __restri
     }
 }
 
+// r = 4, down in {2, 4} (SwinUNetDownscaled, swin_unet.py:366-379): separable form of the kernel above.
+// One block = a TO x TO output tile of one colour plane: the clamped 4x pixels it needs are gathered once into shared
+// memory (8-byte loads: the 4 dx of a token row are contiguous), then a horizontal and a vertical pass with per-row /
+// per-column tap tables (ATen upsample_bicubic2d_aa weights incl. border renormalisation): 2*4*down FMAs per output
+// instead of (4*down)^2 taps with index arithmetic each.  Same summation order as ATen (horizontal first).
+template <int DOWN>
+__global__ void __launch_bounds__(256) to_image_down_kernel(const __half* __restrict__ y, __half* __restrict__ z, int Hs, int Ws) {
+    constexpr int NT = 4 * DOWN, TO = 64 / DOWN, IN = TO * DOWN + NT;   // taps, output tile, staged input side
+    __shared__ float sP[IN][IN + 1];
+    __shared__ float sH[IN][TO + 1];
+    __shared__ float sWy[TO][NT], sWx[TO][NT];
+    __shared__ int sMinY[TO], sMinX[TO], sSzY[TO], sSzX[TO];
+    const int S_full = Hs * 4, S = S_full / DOWN;
+    const int X0 = blockIdx.x * TO, Y0 = blockIdx.y * TO, c = blockIdx.z % 3, b = blockIdx.z / 3;
+    const int tid = threadIdx.x;
+    if (tid < 2 * TO) {
+        const bool isx = tid >= TO;
+        const int o = (isx ? X0 : Y0) + (isx ? tid - TO : tid);
+        const float scale = (float)DOWN, support = 2.f * scale, inv = 1.f / scale;
+        const float ctr = scale * ((float)min(o, S - 1) + 0.5f);
+        const int mn = max((int)(ctr - support + 0.5f), 0), sz = min((int)(ctr + support + 0.5f), S_full) - mn;
+        float w[NT], t = 0.f;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            w[k] = k < sz ? cubic_aa(((float)(k + mn) - ctr + 0.5f) * inv) : 0.f;
+            t += w[k];
+        }
+        const int i = isx ? tid - TO : tid;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) (isx ? sWx : sWy)[i][k] = w[k] / t;
+        (isx ? sMinX : sMinY)[i] = mn;
+        (isx ? sSzX : sSzY)[i] = sz;
+    }
+    __syncthreads();
+    const int ry0 = sMinY[0], rx0 = sMinX[0];
+    const int rx0a = rx0 & ~3;                                         // token-aligned start column
+    const __half* yb = y + (size_t)b * Hs * Ws * 48 + c * 16;
+    // gather: rows ry0 .. ry0+IN-1, columns rx0a .. in groups of 4 (one token row segment = 8 bytes)
+    constexpr int G = (IN + 3) / 4 + 1;
+    for (int i = tid; i < IN * G; i += 256) {
+        const int r = i / G, gq = i - r * G;
+        const int py = min(ry0 + r, S_full - 1), px = rx0a + 4 * gq;
+        uint2 raw = make_uint2(0, 0);
+        if (px < S_full) raw = __ldg(reinterpret_cast<const uint2*>(yb + ((size_t)(py >> 2) * Ws + (px >> 2)) * 48 + (py & 3) * 4));
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+        const float v[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = px + k - rx0;
+            if (col >= 0 && col < IN) sP[r][col] = clamp01(v[k]);      // clamp(z, 0, 1) before the resize (:369)
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < IN * TO; i += 256) {
+        const int r = i / TO, ox = i - r * TO;
+        const int base = sMinX[ox] - rx0, sz = sSzX[ox];
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+            if (k < sz) acc += sP[r][base + k] * sWx[ox][k];
+        sH[r][ox] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < TO * TO; i += 256) {
+        const int oy = i / TO, ox = i - oy * TO;
+        if (Y0 + oy >= S || X0 + ox >= S) continue;
+        const int base = sMinY[oy] - ry0, sz = sSzY[oy];
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+            if (k < sz) acc += sH[base + k][ox] * sWy[oy][k];
+        z[(((size_t)b * 3 + c) * S + Y0 + oy) * S + X0 + ox] = __float2half_rn(clamp01(acc));
+    }
+}
+
 int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws, int cs, int r, int down) {
     NB_CHECK(down == 1 || down == 2 || down == 4, "downscale must be 1, 2 or 4");
     NB_CHECK(Hs == Ws && (Hs * r) % down == 0, "bad ToImage geometry");
@@ -297,6 +373,12 @@ int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws,
     if (r == 4 && down == 1 && cs == 48) {
         const size_t tokens = (size_t)n * Hs * Ws;
         to_image_r4_kernel<<<(unsigned)cdiv64(tokens, 256), 256, 0, st>>>(y, z, n, Hs, Ws);
+    } else if (r == 4 && cs == 48 && down == 2) {
+        const int S = Hs * 2;
+        to_image_down_kernel<2><<<dim3(cdiv(S, 32), cdiv(S, 32), n * 3), 256, 0, st>>>(y, z, Hs, Ws);
+    } else if (r == 4 && cs == 48 && down == 4) {
+        const int S = Hs;
+        to_image_down_kernel<4><<<dim3(cdiv(S, 16), cdiv(S, 16), n * 3), 256, 0, st>>>(y, z, Hs, Ws);
     } else {
         to_image_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(y, z, n, Hs, Ws, cs, r, down);
     }
