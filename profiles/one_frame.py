@@ -1,5 +1,5 @@
 """Render ONE synthetic frame through the engine (for ncu captures; never a bench value).
-usage: python profiles/one_frame.py [4k|1080p] [warp]"""
+usage: python profiles/one_frame.py [4k|1080p] [warp|depth|upcunet]"""
 import os
 import sys
 import torch
@@ -19,6 +19,20 @@ if "warp" in sys.argv:
     for method in ("forward_fill", "backward"):
         for _ in range(3):
             y = stereo_sbs(c, d, 2.0, 0.5, method=method, edge_dilation=[2, 1])
+    torch.cuda.synchronize()
+elif "depth" in sys.argv:
+    from nunif_b200.iw3 import DepthAnythingModel
+    dam = DepthAnythingModel().load_state_dict(synth.depth_anything_v2_state_dict(0), gpu=0)
+    c = torch.stack([synth.synth_image(50 + i, 3, h, w, smooth=False) for i in range(4)]).to(dev)
+    with torch.inference_mode():
+        for _ in range(2):
+            y = dam.infer(c, edge_dilation=[2, 1])
+    torch.cuda.synchronize()
+elif "upcunet" in sys.argv:
+    m = create_model("waifu2x.upcunet", synth.upcunet_state_dict(0), dev)
+    x = synth.synth_image(1, 3, h, w, smooth=False).to(dev)
+    with torch.no_grad():
+        y = tiled_render(x, m, tile_size=256, batch_size=16)
     torch.cuda.synchronize()
 else:
     m = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), dev)
