@@ -258,6 +258,19 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
         }
     }
     NB_CHECK(bn > 0, "no BLOCK_N divides N");
+    if (g_tune[4] == 0 && !shuf) {
+        // small-M launches (ViT tokens of a few frames, coarse DPT levels): prefer narrower tiles until the persistent grid
+        // (m-tiles x n-tiles) covers most SMs; the activation tile is then re-read from L2 by the extra n-tiles
+        const long long m_tiles_est = (long long)p.tiles_x * p.tiles_y * p.B;
+        static const int narrower[] = {128, 96, 64};
+        for (int c : narrower) {
+            if ((long long)(g.N / bn) * m_tiles_est >= (long long)num_sms() * 3 / 4) break;
+            if (c >= bn || g.N % c) continue;
+            const int w = (c % 64 == 0) ? 64 : 32;
+            if (split && g.cout % w) continue;
+            bn = c; cw = w;
+        }
+    }
     p.n_tiles = g.N / bn;
     box[0] = BK; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
     GemmMaps maps;

@@ -1,6 +1,6 @@
 // Shifted-window attention core on tensor cores (mma.sync m16n8k16, fp16 in / fp32 accumulate).
 //
-// One CTA per 6x6 window, one warp per head (6 warps), 4 CTAs per SM.  q/k/v rows are staged with
+// One CTA per 6x6 window, one warp per head (6 warps), 4 CTAs per SM (6 for d = 16).  q/k/v rows are staged with
 // cp.async (16-byte LDGSTS, no register round trip).  The 36 tokens are padded to 48 MMA rows by clamping
 // the row index (padded keys are masked by select, padded probabilities are exactly 0):
 //   S = (Q*scale) K^T : M=48 (3 m16 tiles), N=48 (6 n8 tiles), K=d (d/16 steps)
@@ -191,7 +191,7 @@ __device__ __forceinline__ void attn_mtile(const AttnCtx<D>& cx, int mt) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(192, 4) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
+__global__ void __launch_bounds__(192, D == 16 ? 6 : 4) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
                                                                    __half* __restrict__ out, int H, int W, int shift,
                                                                    size_t plane) {
     constexpr int C = D * HEADS;
@@ -308,7 +308,7 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_
     // 55 KB per layer, are re-read by every window and should hit there).  g_tune[6] overrides the percentage.
     if (C == 96) {
         static int cfg = -1;
-        const int want = g_tune[6] > 0 ? g_tune[6] : 44;
+        const int want = g_tune[6] > 0 ? g_tune[6] : 72;   // 6 CTAs x 23.6 KB
         if (cfg != want) {
             NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>()));
             NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
