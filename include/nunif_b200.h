@@ -227,6 +227,14 @@ int nb200_da_preprocess_size(int H, int W, int lower_bound, int max_aspect_ratio
 int nb200_da_preprocess(const float* x, int B, int H, int W, int new_h, int new_w, float* out,
                         void* stream);
 
+/* ZoeDepth batch_preprocess (iw3/zoedepth_model.py:30-85): size rule (host integers) and the fused
+ * antialiased resize + reflection pad (nunif/modules/reflection_pad2d.py:57-68) + clamp + normalise:
+ * x [B][3][H][W] -> out [B][3][frame_h + 2*pad_h][frame_w + 2*pad_w] (== new_h x new_w in landscape). */
+int nb200_zoe_preprocess_size(int H, int W, int h_height, int v_height, int mod, int* new_h,
+                              int* new_w, int* pad_h, int* pad_w, int* frame_h, int* frame_w);
+int nb200_zoe_preprocess(const float* x, int B, int H, int W, int frame_h, int frame_w, int pad_h,
+                         int pad_w, float* out, void* stream);
+
 /* Kernel-class device timing (CUDA events around every launch of this library) used by
  * bench.py for the live roofline figure.  report writes a JSON object
  * {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...} and synchronises the device. */

@@ -15,3 +15,4 @@ from .stereo import stereo_sbs  # noqa: F401
 from .frames import hwc_to_chw_float, chw_float_to_hwc  # noqa: F401
 from .depth_anything_preprocess import batch_preprocess, preprocess_size  # noqa: F401
 from .depth_anything_model import DepthAnythingModel, DepthAnythingNet, batch_infer  # noqa: F401
+from . import zoedepth_preprocess  # noqa: F401

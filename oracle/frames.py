@@ -80,3 +80,42 @@ def batch_preprocess(x, lower_bound=392, max_aspect_ratio=4, limit_resolution=Fa
     mean = np.array([0.485, 0.456, 0.406], dtype=np.float32).reshape(1, 3, 1, 1)
     stdv = np.array([0.229, 0.224, 0.225], dtype=np.float32).reshape(1, 3, 1, 1)
     return (y - mean) / stdv
+
+
+def zoe_preprocess_size(H, W, h_height=384, v_height=512, mod=32):
+    """iw3/zoedepth_model.py:30-71 -> (new_h, new_w, pad_h, pad_w, frame_h, frame_w)."""
+    target = h_height if W > H else v_height
+    if target < H:
+        new_h = target
+        new_w = int(new_h / H * W)
+        if new_w % mod != 0:
+            new_w += mod - new_w % mod
+        if new_h % mod != 0:
+            new_h += mod - new_h % mod
+    else:
+        new_h, new_w = H, W
+        new_w -= new_w % mod
+        new_h -= new_h % mod
+    pad_src_h, pad_src_w = int((H * 0.5) ** 0.5 * 3), int((W * 0.5) ** 0.5 * 3)
+    sh, sw = pad_src_h / (H + pad_src_h * 2), pad_src_w / (W + pad_src_w * 2)
+    if new_h > new_w:
+        pad_h = round(new_h * sh)
+        frame_h = new_h - pad_h * 2
+        frame_w = int(W * (frame_h / H))
+        frame_w += frame_w % 2
+        pad_w = (new_h - frame_w) // 2
+    else:
+        pad_h, pad_w = round(new_h * sh), round(new_w * sw)
+        frame_h, frame_w = new_h - pad_h * 2, new_w - pad_w * 2
+    return new_h, new_w, pad_h, pad_w, frame_h, frame_w
+
+
+def zoe_batch_preprocess(x, h_height=384, v_height=512, mod=32):
+    """zoedepth_model.py:30-85: AA resize, reflection pad (reflection_pad2d_loop == periodic mirror extension, which is
+    what numpy's mode="reflect" produces for pads larger than the image), clamp, (x - 0.5) / 0.5."""
+    H, W = x.shape[-2:]
+    _, _, ph, pw, fh, fw = zoe_preprocess_size(H, W, h_height, v_height, mod)
+    y = resize_bilinear_aa(x, fh, fw)
+    y = np.pad(y, ((0, 0), (0, 0), (ph, ph), (pw, pw)), mode="reflect")
+    y = np.clip(y, 0, 1)
+    return ((y - np.float32(0.5)) / np.float32(0.5)).astype(np.float32), ph, pw

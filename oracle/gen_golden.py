@@ -224,6 +224,17 @@ def gen_frames():
             y = batch_preprocess(torch.zeros(1, 3, H, W), lower_bound=lb, limit_resolution=lim)
             sizes.append((H, W, lb, int(lim), y.shape[2], y.shape[3]))
     out["sizes"] = np.array(sizes, dtype=np.int64)
+    # ZoeDepth batch_preprocess (iw3/zoedepth_model.py:30-85)
+    from iw3.zoedepth_model import batch_preprocess as zoe_prep
+    y, ph, pw = zoe_prep(x.clone(), h_height=96, v_height=128)
+    out["zoe_land"], out["zoe_land_pad"] = y, np.array([ph, pw])
+    y, ph, pw = zoe_prep(xt.clone(), h_height=96, v_height=128)
+    out["zoe_port"], out["zoe_port_pad"] = y, np.array([ph, pw])
+    zs = []
+    for (H, W) in ((1080, 1920), (2160, 3840), (720, 1280), (480, 854), (1920, 1080), (300, 300), (200, 3000), (393, 699), (100, 64)):
+        y, ph, pw = zoe_prep(torch.zeros(1, 3, H, W))
+        zs.append((H, W, y.shape[2], y.shape[3], ph, pw))
+    out["zoe_sizes"] = np.array(zs, dtype=np.int64)
     save("frames", **out)
 
 

@@ -90,3 +90,13 @@ def test_da_preprocess_size_host_rule_bit_exact():
     for H, W, lb, lim, nh, nw in g["sizes"]:
         assert preprocess_size(int(H), int(W), int(lb), 4, bool(lim)) == (int(nh), int(nw)), (H, W, lb, lim)
     assert preprocess_size(1080, 1920) == (392, 686)
+
+
+def test_zoe_preprocess_size_host_rule_bit_exact():
+    """nb200_zoe_preprocess_size (zoedepth_model.py:30-71, incl. Python's round-half-even) against the reference's sizes."""
+    from tests.util import load_golden
+    from nunif_b200.iw3.zoedepth_preprocess import preprocess_size
+    g = load_golden("frames")
+    for H, W, oh, ow, ph, pw in g["zoe_sizes"]:
+        nh, nw, p_h, p_w, fh, fw = preprocess_size(int(H), int(W))
+        assert (fh + 2 * p_h, fw + 2 * p_w, p_h, p_w) == (int(oh), int(ow), int(ph), int(pw)), (H, W)

@@ -56,3 +56,20 @@ def test_da_batch_preprocess_1080p_against_oracle():
     s = stats(got, torch.from_numpy(want))
     log_metric("da_prep_1080p", **s)
     assert s["max"] < 5e-6
+
+
+def test_zoe_batch_preprocess_golden():
+    from nunif_b200.iw3.zoedepth_preprocess import batch_preprocess
+    g = load_golden("frames")
+    for key, src in (("zoe_land", "x"), ("zoe_port", "xt")):
+        got, ph, pw = batch_preprocess(t(g[src], DEV), h_height=96, v_height=128)
+        assert (ph, pw) == tuple(g[key + "_pad"]) and got.shape == g[key].shape
+        s = stats(got, t(g[key]))
+        log_metric(key, **s)
+        assert s["max"] < 5e-6, (key, s)
+    # 4K frame (BASELINE configs[4] geometry: 384x704 with pads 16, 22) against the oracle
+    x = synth.synth_image(12, 3, 2160, 3840, smooth=False).unsqueeze(0)
+    got, ph, pw = batch_preprocess(x.to(DEV))
+    assert got.shape == (1, 3, 384, 704) and (ph, pw) == (16, 22)
+    want, _, _ = ofr.zoe_batch_preprocess(x.numpy())
+    assert stats(got, torch.from_numpy(want))["max"] < 5e-6

@@ -271,3 +271,15 @@ def test_depth_anything_oracle_matches_transformers():
     assert got.shape == want.shape == (2, 14 * grid, 14 * grid)
     assert float(want.std()) > 0.1
     assert float((got - want).abs().max()) < 2e-4 * float(want.abs().max())
+
+
+def test_zoe_preprocess_oracle_matches_reference():
+    from oracle import frames as ofr
+    g = load_golden("frames")
+    for H, W, oh, ow, ph, pw in g["zoe_sizes"]:
+        nh, nw, p_h, p_w, fh, fw = ofr.zoe_preprocess_size(int(H), int(W))
+        assert (fh + 2 * p_h, fw + 2 * p_w, p_h, p_w) == (int(oh), int(ow), int(ph), int(pw)), (H, W)
+    y, ph, pw = ofr.zoe_batch_preprocess(g["x"], 96, 128)
+    assert (ph, pw) == tuple(g["zoe_land_pad"]) and np.abs(y - g["zoe_land"]).max() < 3e-6
+    y, ph, pw = ofr.zoe_batch_preprocess(g["xt"], 96, 128)
+    assert (ph, pw) == tuple(g["zoe_port_pad"]) and np.abs(y - g["zoe_port"]).max() < 3e-6
