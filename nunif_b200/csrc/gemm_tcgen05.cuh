@@ -179,6 +179,41 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaxf(x, 0.f) - a * e;
 }
 
+// The same GELU on two values with packed fp32 instructions (FFMA2 / fma.rn.f32x2, sm_100+): identical IEEE results per
+// lane, but the polynomial, the exponent FMA and the final FMA issue once per PAIR.  On B200 a scalar FFMA already issues
+// at 1/clk/SMSP and FFMA2 at 1 per 2 clk (profiles/r1/ffma2_tput.json), so this does not add FMA throughput - it frees
+// issue slots: the GELU epilogue was issue-bound at ~13 instructions per value, now ~7, next to the MUFU limit
+// (ex2: 8 clk per warp instruction).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const unsigned long long a = pk2(a0, a1);
+    unsigned long long q = ffma2(a, pk2(4.88118734e-04f, 4.88118734e-04f), pk2(-7.19881030e-03f, -7.19881030e-03f));
+    q = ffma2(q, a, pk2(5.21468017e-02f, 5.21468017e-02f));
+    q = ffma2(q, a, pk2(4.59595724e-01f, 4.59595724e-01f));
+    q = ffma2(q, a, pk2(1.15100057e+00f, 1.15100057e+00f));
+    const unsigned long long na = pk2(-a0, -a1);
+    const unsigned long long t = ffma2(q, na, pk2(-1.0f, -1.0f));            // -(q*a) - 1
+    float t0, t1, e0, e1;
+    upk2(t, t0, t1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+    const unsigned long long r = ffma2(na, pk2(e0, e1), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));   // max(x,0) - |x|*e
+    upk2(r, x0, x1);
+}
+
 // activation over a 16-value fragment; `act` is warp-uniform, so the switch is hoisted out of the element loop
 __device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
     switch (act) {
@@ -188,7 +223,7 @@ __device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
             break;
         case ACT_GELU:
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
             break;
         case ACT_RELU:
 #pragma unroll
