@@ -181,9 +181,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // The same GELU on two values with packed fp32 instructions (FFMA2 / fma.rn.f32x2, sm_100+): identical IEEE results per
 // lane, but the polynomial, the exponent FMA and the final FMA issue once per PAIR.  On B200 a scalar FFMA already issues
-// at 1/clk/SMSP and FFMA2 at 1 per 2 clk (profiles/r1/ffma2_tput.json), so this does not add FMA throughput - it frees
-// issue slots: the GELU epilogue was issue-bound at ~13 instructions per value, now ~7, next to the MUFU limit
-// (ex2: 8 clk per warp instruction).
+// at 1/clk/SMSP and FFMA2 at 1 per 2 clk (profiles/r1/ffma2_tput.json), so this adds no FMA throughput, it only frees issue
+// slots (~13 -> ~7.5 instructions per value).  MEASURED SLOWER in the GEMM epilogue (fc1 247 -> 267 us: the register-pair
+// moves and the longer dependent chain cost more than the issue slots save), so apply_act16 uses the scalar gelu_erf;
+// kept for the record of the experiment.
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -222,8 +223,9 @@ __device__ __forceinline__ void apply_act16(float (&v)[16], int act) {
             for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.1f * v[j];
             break;
         case ACT_GELU:
+            // scalar form: the packed-FMA variant below measured 8 % slower on the fc1 shapes (267 vs 247 us)
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
             break;
         case ACT_RELU:
 #pragma unroll
