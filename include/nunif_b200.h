@@ -242,6 +242,7 @@ int nb200_tune_set(int key, int value);   /* GEMM scheduling knobs for profiles/
 int nb200_debug_timeline(void* dev_buf);  /* per-role clock64 timeline of CTA 0 (profiles/gemm_timeline.py) */
 int nb200_profile_enable(int on);
 int nb200_profile_report(char* buf, size_t cap);
+int nb200_profile_dump(char* buf, size_t cap);   /* one CSV line per timed launch: class,ms,work,read_bytes,write_bytes */
 
 #ifdef __cplusplus
 }

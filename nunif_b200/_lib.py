@@ -81,6 +81,7 @@ SIGNATURES = {
     "nb200_debug_timeline": (c_int, [c_void_p]),
     "nb200_profile_enable": (c_int, [c_int]),
     "nb200_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
+    "nb200_profile_dump": (c_int, [c_char_p, c_size_t]),
     "nb200_window_attention_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

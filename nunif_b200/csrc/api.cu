@@ -104,3 +104,22 @@ extern "C" int nb200_profile_report(char* buf, size_t cap) {
     memcpy(buf, s.c_str(), s.size() + 1);
     return 0;
 }
+
+// Per-launch records of the current profile (one CSV line per timed launch: class,ms,work,read_bytes,write_bytes);
+// profiles/launch_floor.py turns this into the per-launch roofline table.  Synchronises the device.
+extern "C" int nb200_profile_dump(char* buf, size_t cap) {
+    NB_CHECK(buf && cap > 0, "null buffer");
+    NB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::string s;
+    for (auto& r : g_prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+        char tmp[160];
+        snprintf(tmp, sizeof(tmp), "%s,%.6f,%.6e,%.6e,%.6e\n", kCatNames[r.cat], t, r.work, r.rb, r.wb);
+        s += tmp;
+    }
+    NB_CHECK(s.size() + 1 <= cap, "buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
