@@ -219,6 +219,7 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     }
     NB_CHECK(ktap % 32 == 0, "K per tap must be a multiple of 32");
     const int BK = (ktap % 64 == 0) ? 64 : 32;
+    const int BKsel = BK;
     p.cpt = ktap / BK;
     p.tiles_x = cdiv(p.Wo, p.TW);
     p.tiles_y = cdiv(p.Ho, p.TH);
@@ -241,10 +242,21 @@ int conv_gemm(cudaStream_t st, const ConvGemm& g) {
     int bn = 0, cw = 0;
     {
         static const int cands[] = {256, 192, 128, 96, 64, 48, 32, 16};
+        // first choice: the largest BLOCK_N whose weight tile can stay resident in shared memory next to >= 3 activation
+        // stages and the epilogue staging (residual launches stage twice as much); else the largest valid one
+        const int Ktot = p.taps * ktap;
+        int first_bn = 0, first_cw = 0;
         for (int c : cands) {
             const int w = (c % 64 == 0) ? 64 : ((c % 32 == 0) ? 32 : 16);
-            if (g.N % c == 0 && (!shuf || g.cout % w == 0) && (!split || g.cout % c == 0)) { bn = c; cw = w; break; }
+            if (!(g.N % c == 0 && (!shuf || g.cout % w == 0) && (!split || g.cout % c == 0))) continue;
+            if (!first_bn) { first_bn = c; first_cw = w; }
+            const long long stg = (long long)(g.res ? 3 * 2 : 4) * 128 * w * 2 + c * 4;
+            const long long bres = (long long)Ktot * (((c * BKsel * 2 + 1023) / 1024) * 1024) / BKsel;
+            // (only 64-column-chunk tiles of >= 128 columns are considered worth the extra n-tiles: fc2 with K = 384 is faster
+            //  streaming a 192-wide weight tile than resident at 96, profiles/r1/gemm_bench_v4.json)
+            if (c >= 128 && w == 64 && bres + 3LL * 128 * BKsel * 2 + stg <= PG_SMEM_BUDGET) { bn = c; cw = w; break; }
         }
+        if (!bn) { bn = first_bn; cw = first_cw; }
         // epilogue-heavy launches (GELU): narrower tiles give a 4-deep TMEM accumulator ring, so the quads
         // rarely wait for the MMA (profiles/r1/timeline_fc1_*.txt); chunks never straddle a split plane (cout % 64 == 0)
         // residual launches with K = N = 192 (the Swin proj Linear): 64-wide tiles keep 24 KB of weights resident instead

@@ -161,6 +161,19 @@ static Lin pack_stem(Packer& pk, const std::string& name, int cout, int cout_pad
                 wv[(size_t)(k * 3 + ci) * cout_pad + co] = __half2float(__float2half_rn(w[((size_t)co * 3 + ci) * 9 + k]));
             }
     memcpy(bv.data(), b, (size_t)cout * 4);
+    // ... followed by the same weights as fp16 mma.sync B fragments for stem_conv_mma_kernel:
+    // [ks (3)][nt (cout_pad/8)][n (8)][k (16)] with k -> tap = ks*4 + k/4, ci = k%4 (ci == 3 and taps >= 9 are zero)
+    const size_t nf = wv.size();
+    wv.resize(nf + (size_t)24 * cout_pad, 0.f);
+    __half* frag = reinterpret_cast<__half*>(wv.data() + nf);
+    for (int ks = 0; ks < 3; ++ks)
+        for (int nt = 0; nt < cout_pad / 8; ++nt)
+            for (int nn = 0; nn < 8; ++nn)
+                for (int k = 0; k < 16; ++k) {
+                    const int tap = ks * 4 + k / 4, ci = k % 4;
+                    const float v = (tap < 9 && ci < 3) ? wv[(size_t)(tap * 3 + ci) * cout_pad + nt * 8 + nn] : 0.f;
+                    frag[(((size_t)ks * (cout_pad / 8) + nt) * 8 + nn) * 16 + k] = __float2half_rn(v);
+                }
     l.w = pk.add_f32(wv);
     l.b = pk.add_f32(bv);
     return l;

@@ -66,9 +66,102 @@ __global__ void __launch_bounds__(128) stem_conv3x3_kernel(const __half* __restr
     }
 }
 
+// Tensor-core version (production path): K = 9 taps x 4 (3 channels + a zero) = 36 -> 3 k16 steps of mma.sync.m16n8k16.
+// One block = 2 output rows x 64 columns (8 warps x 16 pixels); the 4 x 66 input window is staged in shared memory
+// (16 B per NHWC8 pixel, so every A-fragment register is one 4-byte load: tap = ks*4 + t4/2 (+2), channel pair = (t4&1)*2),
+// B fragments are pre-packed at load time (model.cu pack_stem) and copied with 16-byte loads; the warp's 16 x COUT tile is
+// staged through shared memory so that global stores are 16 bytes per lane.  ~10 instructions per pixel instead of ~2200:
+// the SIMT kernel above reached 32 % of the fp32 FMA peak (153 us per 16-tile batch), this one is bound by its
+// 0.15 GB of output.
+template <int COUT_PAD>
+__global__ void __launch_bounds__(256) stem_conv_mma_kernel(const __half* __restrict__ x, const float* __restrict__ wt,
+                                                            const float* __restrict__ bias, __half* __restrict__ out, int Hi, int Wi,
+                                                            int ldo) {
+    constexpr int NT = COUT_PAD / 8, WC = 66;
+    __shared__ __align__(16) __half sB[3 * NT * 128];
+    __shared__ __align__(16) __half sX[4 * WC * 8];
+    __shared__ __align__(16) __half sO[8][16][COUT_PAD + 8];
+    __shared__ float sBias[COUT_PAD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int Ho = Hi - 2, Wo = Wi - 2;
+    const int j0 = blockIdx.x * 64, oy0 = blockIdx.y * 2, b = blockIdx.z;
+    {
+        const uint4* frag = reinterpret_cast<const uint4*>(wt + 27 * COUT_PAD);
+        for (int i = tid; i < 3 * NT * 16; i += 256) reinterpret_cast<uint4*>(sB)[i] = __ldg(frag + i);
+        if (tid < COUT_PAD) sBias[tid] = bias[tid];
+    }
+    const __half* xb = x + (size_t)b * Hi * Wi * 8;
+    for (int i = tid; i < 4 * WC; i += 256) {
+        const int col = i % WC, r = i / WC;
+        const int iy = oy0 + r, ix = j0 + col;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy < Hi && ix < Wi) v = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)iy * Wi + ix) * 8));
+        reinterpret_cast<uint4*>(sX)[i] = v;
+    }
+    __syncthreads();
+    const int lrow = warp >> 2, lj = (warp & 3) * 16, oy = oy0 + lrow;
+    if (oy >= Ho || j0 + lj >= Wo) return;
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        // k = 2*t4 (+8): tap = ks*4 + (t4 >> 1) (+2), channels (t4 & 1)*2, +1
+        const int tapa = ks * 4 + (t4 >> 1), tapb = tapa + 2, ch = (t4 & 1) * 2;
+        uint32_t a[4] = {0u, 0u, 0u, 0u};
+        if (tapa < 9) {
+            const __half* p = sX + ((lrow + tapa / 3) * WC + lj + g + tapa % 3) * 8 + ch;
+            a[0] = *reinterpret_cast<const uint32_t*>(p);
+            a[1] = *reinterpret_cast<const uint32_t*>(p + 64);     // pixel + 8
+        }
+        if (tapb < 9) {
+            const __half* p = sX + ((lrow + tapb / 3) * WC + lj + g + tapb % 3) * 8 + ch;
+            a[2] = *reinterpret_cast<const uint32_t*>(p);
+            a[3] = *reinterpret_cast<const uint32_t*>(p + 64);
+        }
+        const __half* wb = sB + ks * NT * 128 + g * 16 + 2 * t4;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wb + nt * 128), b1 = *reinterpret_cast<const uint32_t*>(wb + nt * 128 + 8);
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+        }
+    }
+    // bias + LeakyReLU(0.1) -> fp16, staged per warp, then 16-byte stores (one output pixel row = COUT_PAD*2 bytes)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float b0 = sBias[nt * 8 + 2 * t4], b1 = sBias[nt * 8 + 2 * t4 + 1];
+        float v0 = acc[nt][0] + b0, v1 = acc[nt][1] + b1, v2 = acc[nt][2] + b0, v3 = acc[nt][3] + b1;
+        v0 = v0 > 0.f ? v0 : 0.1f * v0; v1 = v1 > 0.f ? v1 : 0.1f * v1;
+        v2 = v2 > 0.f ? v2 : 0.1f * v2; v3 = v3 > 0.f ? v3 : 0.1f * v3;
+        *reinterpret_cast<__half2*>(&sO[warp][g][nt * 8 + 2 * t4]) = __floats2half2_rn(v0, v1);
+        *reinterpret_cast<__half2*>(&sO[warp][g + 8][nt * 8 + 2 * t4]) = __floats2half2_rn(v2, v3);
+    }
+    __syncwarp();
+    constexpr int VPR = COUT_PAD / 8;                          // 16-byte vectors per pixel
+    for (int i = lane; i < 16 * VPR; i += 32) {
+        const int r = i / VPR, v = i - r * VPR;
+        const int ox = j0 + lj + r;
+        if (ox < Wo)
+            *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * ldo + v * 8) = *reinterpret_cast<const uint4*>(&sO[warp][r][v * 8]);
+    }
+}
+
+extern int g_tune[8];  // gemm.cu; [7] != 0 selects the SIMT stem / tail kernels (tests)
+
 int stem_conv3x3(cudaStream_t st, const __half* x, const float* wt, const float* bias, __half* out, int n, int Hi, int Wi,
                  int cout_pad, int ldo) {
     NB_CHECK(ldo >= cout_pad && ldo % 8 == 0, "bad output stride");
+    if (g_tune[7] == 0 && n <= 65535 && (cout_pad == 64 || cout_pad == 32)) {
+        const int Ho = Hi - 2, Wo = Wi - 2;
+        ProfScope ps(st, PC_STEM, (double)n * Hi * Wi * 16 + (double)n * Ho * Wo * ldo * 2, (double)n * Hi * Wi * 16, (double)n * Ho * Wo * cout_pad * 2);
+        const dim3 grid(cdiv(Wo, 64), cdiv(Ho, 2), n);
+        if (cout_pad == 64) stem_conv_mma_kernel<64><<<grid, 256, 0, st>>>(x, wt, bias, out, Hi, Wi, ldo);
+        else stem_conv_mma_kernel<32><<<grid, 256, 0, st>>>(x, wt, bias, out, Hi, Wi, ldo);
+        NB_LAUNCHED();
+        return 0;
+    }
     const size_t total = (size_t)n * (Hi - 2) * (Wi - 2);
     const unsigned blocks = (unsigned)cdiv64(total, 128);
     ProfScope ps(st, PC_STEM, (double)n * Hi * Wi * 16 + (double)total * ldo * 2);

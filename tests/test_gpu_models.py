@@ -72,6 +72,20 @@ def test_cunet_tail_tensor_core_and_simt_kernels_agree(name, up):
     assert stats(a, b)["max"] < 2e-3, stats(a, b)
 
 
+def test_swin_stem_tensor_core_and_simt_kernels_agree():
+    from nunif_b200 import _lib
+    from nunif_b200.nunif.models import create_model
+    m = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), DEV)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(3)).to(DEV)
+    a = m(x).float()
+    _lib.lib().nb200_tune_set(7, 1)
+    try:
+        b = m(x).float()
+    finally:
+        _lib.lib().nb200_tune_set(7, 0)
+    assert stats(a, b)["max"] < 2e-3, stats(a, b)
+
+
 @pytest.mark.parametrize("name,up", [("upcunet", True), ("cunet", False)])
 def test_cunet_tiled_render(name, up):
     from nunif_b200.nunif.models import create_model
