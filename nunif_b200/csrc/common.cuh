@@ -63,6 +63,11 @@ struct ProfScope {
 int tile_gather_blend_rows(const void* z_all, int C, const ::nb200_tile_config* cfg, int scale, int offset, int tile_size,
                            int blend_size, float* out, int y0, int y1, void* stream);
 
+// Programmatic dependent launch (sm_90+): a kernel that executes this lets a PDL-attributed successor (the persistent
+// GEMM, gemm.cu launch_p) be scheduled as soon as every CTA of this grid has issued it or exited; the successor blocks in
+// griddepcontrol.wait until this grid has completed and flushed.  A no-op for ordinary successors.
+#define NB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -328,7 +328,7 @@ static int launch_tail_mma(cudaStream_t st, const __half* x, const float* wt, co
     return 0;
 }
 
-extern int g_tune[8];  // gemm.cu; [7] != 0 selects the SIMT tail kernel (tests)
+extern int g_tune[16];  // gemm.cu; [7] != 0 selects the SIMT tail kernel (tests)
 
 int tail_conv(cudaStream_t st, int mode, int epi, const __half* x, const float* wt, const float* bias, __half* out,
               const __half* z1, int n, int Hi, int Wi, int z1H, int z1W, int clip) {

@@ -39,6 +39,7 @@ __device__ __forceinline__ float ex2(float x) {
 // ------------------------------------------------------------------------------------------ patch embedding
 __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ x, __half* __restrict__ A, int B, int H, int W,
                                                             int ph, int pw, int kpad) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     const long long total = (long long)B * ph * pw * kpad;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -72,6 +73,7 @@ template <int DIM>
 __global__ void __launch_bounds__(256) add_layernorm_kernel(float* __restrict__ X, const __half* __restrict__ delta,
                                                              const float* __restrict__ w, const float* __restrict__ b,
                                                              __half* __restrict__ out, long long rows) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     constexpr int V = DIM / 128;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(float* __restrict__ 
 constexpr int FA_D = 64, FA_BM = 64, FA_BN = 64, FA_LD = FA_D + 8;   // +8 halves: conflict-free fragment loads
 
 __global__ void __launch_bounds__(128) flash_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int N, int heads) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     extern __shared__ __align__(16) unsigned char fa_smem[];
     __half* sq = reinterpret_cast<__half*>(fa_smem);            // [64][72]  (later: the output tile)
     __half* sk = sq + FA_BM * FA_LD;                            // [2][64][72]
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(128) flash_attention_kernel(const __half* __re
 // ------------------------------------------------------------------------------------------ DPT head helpers
 __global__ void __launch_bounds__(256) relu_add_kernel(const uint4* __restrict__ x, const uint4* __restrict__ x0, uint4* __restrict__ y,
                                                         uint4* __restrict__ s, long long n8) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n8) return;
     const uint4 a = x[i];
@@ -279,6 +283,7 @@ __global__ void __launch_bounds__(256) relu_add_kernel(const uint4* __restrict__
 // ATen upsample_bilinear2d, align_corners=True: src = dst * (in-1)/(out-1); fp32 interpolation, fp16 storage
 __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const __half* __restrict__ x, __half* __restrict__ out, int B, int h, int w,
                                                                  int C8, int H, int W, float sy, float sx) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     const long long total = (long long)B * H * W * C8;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -311,6 +316,7 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const __half* __
 
 __global__ void __launch_bounds__(256) depth_to_space4_kernel(const __half* __restrict__ T, __half* __restrict__ out, int B, int h, int w,
                                                                int c, int cpad) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     const long long total = (long long)B * 4 * h * 4 * w * cpad;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(256) depth_to_space4_kernel(const __half* __re
 
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const __half* __restrict__ x, __half* __restrict__ A, int B, int h, int w, int C,
                                                          int ho, int wo) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     const int C8 = C / 8;
     const long long total = (long long)B * ho * wo * 9 * C8;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

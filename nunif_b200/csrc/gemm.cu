@@ -83,9 +83,10 @@ constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*bar
 
 // tuning knobs for profiles/gemm_bench.py (nb200_tune_set); defaults are the shipped configuration
 unsigned long long* g_timeline = nullptr;
-int g_tune[8] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, /*3 force gather backward warp*/ 0,
+int g_tune[16] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, /*3 force gather backward warp*/ 0,
                  /*4 forced BLOCK_N*/ 0, /*5 disable GELU->128 rule*/ 0,
-                 /*6 attention smem carveout %*/ 0, /*7 SIMT tail convs*/ 0};
+                 /*6 attention smem carveout %*/ 0, /*7 SIMT stem / tail convs*/ 0,
+                  /*8 programmatic dependent launch of the GEMMs*/ 1, 0, 0, 0, 0, 0, 0, 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {
@@ -95,7 +96,17 @@ static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, in
         configured = (int)smem;
     }
     pp.stages = stages;
-    gemm_conv_persistent<BN, BK, RES><<<grid, PG_THREADS, smem, st>>>(maps, pp);
+    // programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream drains (that kernel
+    // must have executed griddepcontrol.launch_dependents); its prologue (barriers, TMEM, tensor-map prefetch, the static
+    // weight tile) then overlaps the predecessor's tail, and the producer warp blocks in griddepcontrol.wait before the first
+    // activation load.  Without an early trigger in the predecessor this degenerates to ordinary stream order.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(PG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_tune[8] ? 1 : 0;
+    NB_CUDA(cudaLaunchKernelEx(&cfg, gemm_conv_persistent<BN, BK, RES>, maps, pp));
     NB_LAUNCHED();
     return 0;
 }
@@ -363,7 +374,7 @@ extern "C" int nb200_debug_timeline(void* dev_buf) {
 
 // profiling knobs (see g_tune in this file); not part of the reference-facing API
 extern "C" int nb200_tune_set(int key, int value) {
-    NB_CHECK(key >= 0 && key < 8, "bad key");
+    NB_CHECK(key >= 0 && key < 16, "bad key");
     g_tune[key] = value;
     return 0;
 }

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
         mbar_init(b_full, 1);
         fence_barrier_init();
     }
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();   // the next GEMM of the stream may start its prologue while this grid drains
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + BLOCK_N) sBias[threadIdx.x - 64] = p.bias ? __ldg(p.bias + n0 + (threadIdx.x - 64)) : 0.f;
     tc_fence_before();
@@ -138,6 +139,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                 mbar_expect_tx(b_full, (uint32_t)(k_iters * Cfg::B_BYTES));
                 for (int it = 0; it < k_iters; ++it) tma_load_2d(&maps.b, b_full, sB + it * B_BYTES, it * BK, n0);
             }
+            // everything above touched only launch constants (weights, bias, tensor maps); activations and residuals are
+            // produced by the preceding kernels of the stream
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             TileWalk tw;
             tw.init(m_first, pp.grid_m, p.tiles_x, p.tiles_y);
             int s = 0, rq = 0;

@@ -19,7 +19,7 @@
 
 namespace nb200 {
 
-extern int g_tune[8];  // gemm.cu (nb200_tune_set)
+extern int g_tune[16];  // gemm.cu (nb200_tune_set)
 
 namespace {
 constexpr int WS = 6, WTOK = 36, WPAD = 48, HEADS = 6;
@@ -194,6 +194,7 @@ template <int D>
 __global__ void __launch_bounds__(192, D == 16 ? 6 : 4) window_attention_mma_kernel(const __half* __restrict__ qkv, const float4* __restrict__ bias_frag,
                                                                    __half* __restrict__ out, int H, int W, int shift,
                                                                    size_t plane) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     constexpr int C = D * HEADS;
     constexpr int LD = C + 8;  // padded row: (C+8)*2 bytes = 4 words mod 32 banks -> conflict-free fragment loads
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -77,6 +77,7 @@ template <int COUT_PAD>
 __global__ void __launch_bounds__(256) stem_conv_mma_kernel(const __half* __restrict__ x, const float* __restrict__ wt,
                                                             const float* __restrict__ bias, __half* __restrict__ out, int Hi, int Wi,
                                                             int ldo) {
+    if (threadIdx.x == 0) NB_PDL_TRIGGER();
     constexpr int NT = COUT_PAD / 8, WC = 66;
     __shared__ __align__(16) __half sB[3 * NT * 128];
     __shared__ __align__(16) __half sX[4 * WC * 8];
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) stem_conv_mma_kernel(const __half* __rest
     }
 }
 
-extern int g_tune[8];  // gemm.cu; [7] != 0 selects the SIMT stem / tail kernels (tests)
+extern int g_tune[16];  // gemm.cu; [7] != 0 selects the SIMT stem / tail kernels (tests)
 
 int stem_conv3x3(cudaStream_t st, const __half* x, const float* wt, const float* bias, __half* out, int n, int Hi, int Wi,
                  int cout_pad, int ldo) {

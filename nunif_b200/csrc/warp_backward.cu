@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) backward_warp_row_kernel(BwParams p, int 
     }
 }
 
-extern int g_tune[8];  // gemm.cu; [3] != 0 forces the gather-from-global kernel (tests)
+extern int g_tune[16];  // gemm.cu; [3] != 0 forces the gather-from-global kernel (tests)
 
 template <int COMPOSE>
 static int launch_bw_row(const BwParams& p, size_t smem, int S, int vec_ok, cudaStream_t st) {
