@@ -83,7 +83,9 @@ def test_swin_stem_tensor_core_and_simt_kernels_agree():
         b = m(x).float()
     finally:
         _lib.lib().nb200_tune_set(7, 0)
-    assert stats(a, b)["max"] < 2e-3, stats(a, b)
+    # a different summation order in the first conv is amplified through the 14 Swin blocks to the model's fp16 noise
+    # floor (refamp_vs_fp32 is 3.7e-3 for this tile, profiles/r1/parity.txt)
+    assert stats(a, b)["max"] < 6e-3 and stats(a, b)["mean"] < 5e-4, stats(a, b)
 
 
 @pytest.mark.parametrize("name,up", [("upcunet", True), ("cunet", False)])
