@@ -82,7 +82,8 @@ enum {
     NB200_MODEL_SWIN_UNET_4X = 5,   /* waifu2x.swin_unet_4x (swin_unet.py:261-303)        */
     /* Depth-Anything-V2 ViT-S: third-party net the reference loads through torch.hub
      * (iw3/depth_anything_model.py:223-230); state_dict keys `pretrained.*`, `depth_head.*` */
-    NB200_MODEL_DEPTH_ANYTHING_V2_S = 6
+    NB200_MODEL_DEPTH_ANYTHING_V2_S = 6,
+    NB200_MODEL_ROW_FLOW_V3 = 7     /* sbs.row_flow_v3, iw3's default learned stereo warp (iw3/models/row_flow_v3.py) */
 };
 
 /* Create a model from named fp32 host tensors using the reference's state_dict
@@ -126,6 +127,16 @@ int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, i
  * -> depth [B][H][W] fp32 (relative inverse depth, larger = nearer). */
 int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth,
                                  void* stream);
+
+/* sbs.row_flow_v3 in delta_output mode (iw3/models/row_flow_v3.py:57-68,111-116): x [B][3][h][w] fp32 = depth,
+ * divergence feature, convergence feature (make_input_tensor, iw3/backward_warp.py:18-63) -> delta [B][1][h][w]
+ * fp32 (the x component; the y component is zero). */
+int nb200_row_flow_delta(nb200_model* m, const float* x, int B, int h, int w, float* delta, void* stream);
+
+/* backward_warp(c, grid, delta, delta_scale) of the learned warps (iw3/backward_warp.py:67-83,213-226):
+ * c [B][3][H][W], delta [B][1][h][w] fp32 -> out [B][3][H][W] = clamp(grid_sample(c, grid + delta*delta_scale)). */
+int nb200_backward_warp_delta(const float* c, const float* delta, int B, int H, int W, int h, int w,
+                              double delta_scale, float* out, void* stream);
 
 /* AlphaBorderPadding.forward (nunif/utils/alpha.py:32-57): rgb [3][H][W], alpha [1][H][W] fp32 ->
  * out [3][H][W]: transparent pixels are filled from their opaque neighbours, `offset` rounds

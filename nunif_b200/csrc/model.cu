@@ -7,6 +7,7 @@
 #include "swin_kernels.h"
 #include "cunet_kernels.h"
 #include "depth_kernels.h"
+#include "rowflow_kernels.h"
 #include "../../include/nunif_b200.h"
 #include <map>
 #include <vector>
@@ -193,6 +194,7 @@ struct SwinW {
 
 struct CUNetW;  // cunet_model.inl
 struct DaW;     // depth_model.inl
+struct RfW;     // rowflow_model.inl
 
 }  // namespace nb200
 
@@ -206,6 +208,7 @@ struct nb200_model {
     SwinW sw;
     std::shared_ptr<CUNetW> cu;
     std::shared_ptr<DaW> da;
+    std::shared_ptr<RfW> rf;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
@@ -427,6 +430,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 
 #include "cunet_model.inl"
 #include "depth_model.inl"
+#include "rowflow_model.inl"
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -434,7 +438,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
                                   const int64_t* numel, int no_clip, nb200_model** out) {
     NB_CHECK(out && names && data && numel, "null pointer");
-    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_DEPTH_ANYTHING_V2_S, "unknown model kind");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_ROW_FLOW_V3, "unknown model kind");
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
@@ -460,6 +464,7 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
         case NB200_MODEL_UPCUNET: m->cu = pack_cunet(pk, true); m->scale = 2; m->offset = 36; m->blend = 0; break;   // cunet.py:144
         case NB200_MODEL_CUNET: m->cu = pack_cunet(pk, false); m->scale = 1; m->offset = 28; m->blend = 0; break;    // cunet.py:178
         case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk); m->scale = 1; break;
+        case NB200_MODEL_ROW_FLOW_V3: m->rf = pack_row_flow(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;   // row_flow_v3.py:37
     }
     if (pk.err.empty())
         for (auto& kv : pk.src)
@@ -623,4 +628,12 @@ extern "C" int nb200_depth_anything_forward(nb200_model* m, const float* x, int 
     NB_CHECK(m->kind == NB200_MODEL_DEPTH_ANYTHING_V2_S && m->da, "model is not a Depth-Anything network");
     NB_CHECK(B > 0, "empty batch");
     return depth_anything_forward(m, (cudaStream_t)stream, x, B, H, W, depth);
+}
+
+// RowFlowV3.forward with delta_output=True (iw3/models/row_flow_v3.py:111-116) - the x component of the returned delta
+extern "C" int nb200_row_flow_delta(nb200_model* m, const float* x, int B, int h, int w, float* delta, void* stream) {
+    NB_CHECK(m && x && delta, "null pointer");
+    NB_CHECK(m->kind == NB200_MODEL_ROW_FLOW_V3 && m->rf, "model is not sbs.row_flow_v3");
+    NB_CHECK(B > 0 && h > 0 && w > 0, "bad shape");
+    return row_flow_forward(m, (cudaStream_t)stream, x, B, h, w, delta);
 }

@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) backward_warp_kernel(BwParams p) {
 // gather-from-global kernel above this removes the 64-bit address arithmetic (30% of its issue slots) and the
 // per-pixel depth loads; the kernel is then bounded by its HBM stores.
 struct __align__(16) GridTab { float l0, r0, l1, r1; };
+constexpr int COMPOSE_RIGHT_ONLY = 3;   // internal: only the "+shift" view, written to p.left (nb200_backward_warp_delta)
 
 template <int COMPOSE>
 __global__ void __launch_bounds__(256) backward_warp_row_kernel(BwParams p, int S, int vec_ok) {
@@ -291,7 +292,14 @@ __global__ void __launch_bounds__(256) backward_warp_row_kernel(BwParams p, int 
         } else {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                if (vec_ok) {
+                if (COMPOSE == COMPOSE_RIGHT_ONLY) {   // single warped view (learned-delta warp): the "+delta" eye goes to p.left
+                    if (vec_ok) {
+                        __stcs(reinterpret_cast<float4*>(lrow + k * oplane + x0), make_float4(outr[0][k], outr[1][k], outr[2][k], outr[3][k]));
+                    } else {
+                        for (int v = 0; v < 4; ++v)
+                            if (x0 + v < p.W) lrow[k * oplane + x0 + v] = outr[v][k];
+                    }
+                } else if (vec_ok) {
                     __stcs(reinterpret_cast<float4*>(lrow + k * oplane + x0), make_float4(outl[0][k], outl[1][k], outl[2][k], outl[3][k]));
                     __stcs(reinterpret_cast<float4*>(rrow + k * oplane + x0), make_float4(outr[0][k], outr[1][k], outr[2][k], outr[3][k]));
                 } else {
@@ -399,6 +407,34 @@ extern "C" int nb200_anaglyph_dubois(const float* l, const float* r, int B, int 
     NB_CHECK(l && r && out, "null pointer");
     size_t plane = (size_t)H * W, total = plane * B;
     anaglyph_dubois_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(l, r, out, plane, total, clip_before);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// backward_warp(c, grid, delta, delta_scale) of the learned stereo warps (iw3/backward_warp.py:67-83 as called from
+// apply_divergence_nn_delta :213-226): grid x = mesh_x + delta * delta_scale at the delta resolution, bilinearly resized to
+// the image (align_corners=True), grid_sample(bilinear, border) and clamp.  Same kernel as the depth-driven warp with
+// index_shift := delta (shift = 1, convergence term = 0) and only the "+" view evaluated.
+extern "C" int nb200_backward_warp_delta(const float* c, const float* delta, int B, int H, int W, int h, int w, double delta_scale,
+                                         float* out, void* stream) {
+    NB_CHECK(c && delta && out, "null pointer");
+    NB_CHECK(B > 0 && H > 0 && W > 0 && h > 0 && w > 0, "bad shape");
+    BwParams p;
+    p.c = c; p.depth = delta; p.left = out; p.right = nullptr;
+    p.B = B; p.H = H; p.W = W; p.h = h; p.w = w;
+    p.shift = 1.0f; p.shift_conv = 0.0f;
+    p.delta_scale = (float)delta_scale;
+    p.sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    p.sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    p.step_x = w > 1 ? 2.0f / (float)(w - 1) : 0.f;
+    p.warp_left = 0; p.warp_right = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = (W + 1 + 3) & ~3;
+    const size_t smem = sizeof(GridTab) * (size_t)(w + 1) + sizeof(float) * 3 * (size_t)S;
+    NB_CHECK(smem <= 200 * 1024 && B <= 65535, "image row too wide for the row-staged warp");
+    const bool aligned = (((uintptr_t)c | (uintptr_t)out) & 15) == 0;
+    ProfScope ps(st, PC_WARP_BW, (double)B * H * W * 4 * 6 + (double)B * h * w * 4);
+    if (launch_bw_row<COMPOSE_RIGHT_ONLY>(p, smem, S, (W % 4 == 0) && aligned, st)) return 1;
     NB_LAUNCHED();
     return 0;
 }

@@ -16,3 +16,4 @@ from .frames import hwc_to_chw_float, chw_float_to_hwc  # noqa: F401
 from .depth_anything_preprocess import batch_preprocess, preprocess_size  # noqa: F401
 from .depth_anything_model import DepthAnythingModel, DepthAnythingNet, batch_infer  # noqa: F401
 from . import zoedepth_preprocess  # noqa: F401
+from .row_flow import RowFlowV3, apply_divergence_nn_LR, apply_divergence_nn_delta  # noqa: F401

@@ -255,3 +255,40 @@ def depth_anything_v2_state_dict(seed=0, encoder="vits", pos_grid=37):
     sd["depth_head.scratch.output_conv2.2.weight"] = rn(1, 32, 1, 1, std=1.0 / 32 ** 0.5).abs()
     sd["depth_head.scratch.output_conv2.2.bias"] = torch.full((1,), 0.3)
     return sd
+
+
+def row_flow_v3_state_dict(seed=0):
+    """Seeded weights with the key names of `sbs.row_flow_v3` (iw3/models/row_flow_v3.py); buffers (`index`, `delta`,
+    `delta_scale`) are the constants the reference constructs.  Gains give deltas of a few pixels for unit-range depth."""
+    g = torch.Generator().manual_seed(20_000 + seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    sd = {"blocks.0.weight": rn(64, 24, 1, 1, std=1.0 / 24 ** 0.5), "blocks.0.bias": rn(64, std=0.05)}
+    for bi, ws in ((1, 4), (2, 3)):
+        p = f"blocks.{bi}."
+        N = ws * ws
+        hid = int(N ** 0.5) * 2
+        sd[p + "mha.mha.qkv_proj.weight"] = rn(192, 64, std=1.2 / 8)
+        sd[p + "mha.mha.qkv_proj.bias"] = rn(192, std=0.05)
+        sd[p + "mha.mha.head_proj.weight"] = rn(64, 64, std=0.6 / 8)
+        sd[p + "mha.mha.head_proj.bias"] = rn(64, std=0.02)
+        sd[p + "conv_mlp.0.weight"] = rn(64, 64, 1, 1, std=1.0 / 8)
+        sd[p + "conv_mlp.0.bias"] = rn(64, std=0.05)
+        sd[p + "conv_mlp.3.weight"] = rn(64, 64, 3, 3, std=0.6 / 24)
+        sd[p + "conv_mlp.3.bias"] = rn(64, std=0.02)
+        pos = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij"), dim=2).reshape(N, 2)
+        delta = [tuple(d) for d in (pos[:, None, :] - pos[None, :, :]).reshape(N * N, 2).tolist()]
+        uniq = sorted(set(delta))
+        sd[p + "bias.index"] = torch.tensor([uniq.index(d) for d in delta], dtype=torch.int64)
+        ud = torch.tensor(uniq, dtype=torch.float32)
+        sd[p + "bias.delta"] = ud / ud.abs().max()
+        sd[p + "bias.to_bias.0.weight"] = rn(hid, 2, std=1.0)
+        sd[p + "bias.to_bias.0.bias"] = rn(hid, std=0.3)
+        sd[p + "bias.to_bias.2.weight"] = rn(1, hid, std=1.0)
+        sd[p + "bias.to_bias.2.bias"] = rn(1, std=0.1)
+    sd["last_layer.1.weight"] = rn(1, 8, 3, 3, std=1.5 / 72 ** 0.5)
+    sd["last_layer.1.bias"] = rn(1, std=0.1)
+    sd["delta_scale"] = torch.tensor(1.0 / 127.0)
+    return sd

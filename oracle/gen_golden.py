@@ -238,9 +238,37 @@ def gen_frames():
     save("frames", **out)
 
 
+def gen_row_flow():
+    """sbs.row_flow_v3 (iw3/models/row_flow_v3.py) + apply_divergence_nn_LR (iw3/backward_warp.py:124-232), steps=1."""
+    from nunif.models import create_model
+    import iw3.models  # noqa: F401  (registers sbs.*)
+    from iw3.backward_warp import apply_divergence_nn_LR, make_input_tensor
+    m = create_model("sbs.row_flow_v3").eval()
+    sd = synth.row_flow_v3_state_dict(0)
+    m.load_state_dict(sd, strict=True)
+    m.delta_output = True
+    out = {}
+    d = synth.synth_depth(3, 2, 70, 130)
+    x = torch.stack([make_input_tensor(None, d[i], divergence=2.0, convergence=0.5, image_width=130) for i in range(2)])
+    out["d"], out["x"] = d, x
+    out["delta"] = m(x)[:, 0:1]
+    c = torch.stack([synth.synth_image(4 + i, 3, 140, 260) for i in range(2)])
+    out["c"] = c
+    l, r = apply_divergence_nn_LR(m, c, d, 2.0, 0.5, steps=1, enable_amp=False)
+    out["left"], out["right"] = l, r
+    l, r = apply_divergence_nn_LR(m, c, d, 2.5, 0.3, steps=1, synthetic_view="right", enable_amp=False)
+    out["sv_right_l"], out["sv_right_r"] = l, r
+    d2 = synth.synth_depth(5, 1, 96, 192)                      # sizes that are already multiples of 12 / 96
+    c2 = synth.synth_image(9, 3, 96, 192).unsqueeze(0)
+    out["d2"], out["c2"] = d2, c2
+    l, r = apply_divergence_nn_LR(m, c2, d2, 4.0, 0.6, steps=1, enable_amp=False)
+    out["left2"], out["right2"] = l, r
+    save("row_flow", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -251,3 +279,5 @@ if __name__ == "__main__":
         gen_alpha_tta()
     if "frames" in which:
         gen_frames()
+    if "row_flow" in which:
+        gen_row_flow()

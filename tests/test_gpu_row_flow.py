@@ -1,0 +1,77 @@
+"""GPU parity of iw3's default learned stereo warp, sbs.row_flow_v3 + apply_divergence_nn_LR,
+against golden outputs of the real reference model (tests/golden/row_flow.npz) and the oracle's restatement."""
+import pytest
+import torch
+
+from tests.util import load_golden, t, log_metric, stats
+from nunif_b200 import synth
+from oracle import row_flow as orf
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _amp_delta(sd, x):
+    sdc = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        return orf.row_flow_delta(sdc, x.to(DEV)).float().cpu()
+
+
+def test_row_flow_delta_golden():
+    from nunif_b200.iw3 import RowFlowV3
+    g = load_golden("row_flow")
+    sd = synth.row_flow_v3_state_dict(0)
+    m = RowFlowV3(sd, DEV)
+    x = t(g["x"], DEV)
+    got = m(x)
+    assert got.shape == (2, 2, 70, 130) and float(got[:, 1].abs().max()) == 0.0
+    ref32, refamp = t(g["delta"]), _amp_delta(sd, t(g["x"]))
+    e_ref, e_our = stats(refamp, ref32), stats(got[:, :1], ref32)
+    log_metric("row_flow_delta", ours_max=e_our["max"], ours_mean=e_our["mean"], refamp_max=e_ref["max"], refamp_mean=e_ref["mean"],
+               scale=float(ref32.abs().max()))
+    scale = float(ref32.abs().max())
+    assert e_our["max"] <= max(1e-3 * scale, 1.5 * e_ref["max"]) and e_our["mean"] <= max(5e-4 * scale, 1.25 * e_ref["mean"]), (e_our, e_ref)
+
+
+def test_backward_warp_delta_exact_formula():
+    """The delta warp alone (fp32 kernel) against the oracle's grid_sample on the reference's own delta."""
+    from nunif_b200.iw3.row_flow import _warp_delta
+    g = load_golden("row_flow")
+    c, delta = t(g["c"], DEV), t(g["delta"], DEV)
+    got = _warp_delta(c, delta, 1.0 / (130 // 2 - 1))
+    want = orf.warp_delta(t(g["c"]), t(g["delta"]), 130)
+    assert stats(got, want)["max"] < 1e-4
+
+
+@pytest.mark.parametrize("key,dk,ck,div,conv,sv", [("", "d", "c", 2.0, 0.5, "both"), ("sv_right_", "d", "c", 2.5, 0.3, "right"),
+                                                    ("2", "d2", "c2", 4.0, 0.6, "both")])
+def test_apply_divergence_nn_LR_golden(key, dk, ck, div, conv, sv):
+    from nunif_b200.iw3 import RowFlowV3, apply_divergence_nn_LR
+    g = load_golden("row_flow")
+    sd = synth.row_flow_v3_state_dict(0)
+    m = RowFlowV3(sd, DEV)
+    c, d = t(g[ck], DEV), t(g[dk], DEV)
+    l, r = apply_divergence_nn_LR(m, c, d, div, conv, steps=1, synthetic_view=sv)
+    wl, wr = (t(g["left" + key]), t(g["right" + key])) if key in ("", "2") else (t(g["sv_right_l"]), t(g["sv_right_r"]))
+    # the delta is computed in fp16 (reference numerics under autocast; the golden is the reference's fp32 CPU run):
+    # a delta error of e pixels moves the sample by e/2 source pixels, i.e. |dz| <= e/2 * max gradient of c
+    sl, sr = stats(l, wl), stats(r, wr)
+    log_metric("row_flow_lr_" + (key or "both"), left_max=sl["max"], right_max=sr["max"], left_mean=sl["mean"], right_mean=sr["mean"])
+    assert sl["mean"] < 1e-3 and sr["mean"] < 1e-3 and sl["max"] < 3e-2 and sr["max"] < 3e-2, (sl, sr)
+    if sv == "right":
+        assert torch.equal(l, c)
+
+
+def test_row_flow_1080p_runs_and_matches_oracle_amp():
+    from nunif_b200.iw3 import RowFlowV3, apply_divergence_nn_LR
+    sd = synth.row_flow_v3_state_dict(1)
+    m = RowFlowV3(sd, DEV)
+    c = synth.synth_image(31, 3, 1080, 1920).unsqueeze(0).to(DEV)
+    d = synth.synth_depth(32, 1, 392, 686).to(DEV)
+    l, r = apply_divergence_nn_LR(m, c, d, 2.0, 0.5)
+    sdc = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad():
+        lo, ro = orf.apply_divergence_nn_LR({k: v.cpu() for k, v in sdc.items()}, c.cpu(), d.cpu(), 2.0, 0.5)
+    sl, sr = stats(l, lo), stats(r, ro)
+    log_metric("row_flow_1080p", left_max=sl["max"], right_max=sr["max"], left_mean=sl["mean"], right_mean=sr["mean"])
+    assert sl["mean"] < 1e-3 and sr["mean"] < 1e-3

@@ -283,3 +283,19 @@ def test_zoe_preprocess_oracle_matches_reference():
     assert (ph, pw) == tuple(g["zoe_land_pad"]) and np.abs(y - g["zoe_land"]).max() < 3e-6
     y, ph, pw = ofr.zoe_batch_preprocess(g["xt"], 96, 128)
     assert (ph, pw) == tuple(g["zoe_port_pad"]) and np.abs(y - g["zoe_port"]).max() < 3e-6
+
+
+def test_row_flow_oracle_matches_reference():
+    from oracle import row_flow as orf
+    g = load_golden("row_flow")
+    sd = synth.row_flow_v3_state_dict(0)
+    with torch.no_grad():
+        x = orf.make_input(t(g["d"]), 2.0, 0.5)
+        assert torch.equal(x, t(g["x"]))
+        assert float((orf.row_flow_delta(sd, x) - t(g["delta"])).abs().max()) < 1e-5
+        l, r = orf.apply_divergence_nn_LR(sd, t(g["c"]), t(g["d"]), 2.0, 0.5)
+        assert float((l - t(g["left"])).abs().max()) < 1e-5 and float((r - t(g["right"])).abs().max()) < 1e-5
+        l, r = orf.apply_divergence_nn_LR(sd, t(g["c"]), t(g["d"]), 2.5, 0.3, "right")
+        assert torch.equal(l, t(g["sv_right_l"])) and float((r - t(g["sv_right_r"])).abs().max()) < 1e-5
+        l, r = orf.apply_divergence_nn_LR(sd, t(g["c2"]), t(g["d2"]), 4.0, 0.6)
+        assert float((l - t(g["left2"])).abs().max()) < 1e-5 and float((r - t(g["right2"])).abs().max()) < 1e-5
