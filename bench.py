@@ -175,8 +175,10 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
     def full(method):
         with torch.inference_mode():
             depth = dam.infer(c, edge_dilation=[2, 1])
-            return stereo_sbs(c, depth, 2.0, 0.5, method=method, edge_dilation=0)
-    for method in ("forward_fill", "backward"):
+            return stereo_sbs(c, depth, 2.0, 0.5, method=method, edge_dilation=0, side_model=rfm)
+    from nunif_b200.iw3 import RowFlowV3
+    rfm = RowFlowV3(synth.row_flow_v3_state_dict(0), dev)
+    for method in ("forward_fill", "backward", "row_flow_v3"):
         for _ in range(3):
             y = full(method)
         torch.cuda.synchronize()

@@ -8,7 +8,7 @@ from ._common import COMPOSE_SBS, COMPOSE_ANAGLYPH
 
 
 def stereo_sbs(c, depth, divergence=2.0, convergence=0.5, method="forward_fill", mapper="none",
-               edge_dilation=0, synthetic_view="both", anaglyph=None):
+               edge_dilation=0, synthetic_view="both", anaglyph=None, side_model=None):
     """c: B,3,H,W frames; depth: B,1,h,w raw model output (larger = nearer).
     dilate_edge -> per-frame min/max -> mapper -> warp -> SBS (B,3,H,2W) or anaglyph (B,3,H,W)."""
     if edge_dilation_is_enabled(edge_dilation):
@@ -27,4 +27,15 @@ def stereo_sbs(c, depth, divergence=2.0, convergence=0.5, method="forward_fill",
         if anaglyph not in (None, "dubois"):
             raise NotImplementedError("fused anaglyph epilogue supports dubois only")
         return apply_divergence_grid_sample(c, depth, divergence, convergence, synthetic_view, compose=compose)
+    if method in {"row_flow_v3", "row_flow"}:
+        # the learned warp (iw3/utils.py:331-340 apply_divergence_nn_LR with args.side_model)
+        if side_model is None:
+            raise ValueError("method row_flow_v3 needs side_model (a nunif_b200.iw3.RowFlowV3)")
+        import torch
+        from .row_flow import apply_divergence_nn_LR
+        l, r = apply_divergence_nn_LR(side_model, c, depth, divergence, convergence, steps=1, synthetic_view=synthetic_view)
+        if anaglyph is not None:
+            from .anaglyph import apply_anaglyph_redcyan
+            return apply_anaglyph_redcyan(l, r, anaglyph)
+        return torch.cat([l, r], dim=3)
     raise ValueError(f"method {method} is not on the B200 hot path")

@@ -17,6 +17,16 @@ def _amp_delta(sd, x):
         return orf.row_flow_delta(sdc, x.to(DEV)).float().cpu()
 
 
+def _oracle_lr_on_device(sdc, c, d, div, conv):
+    """oracle.row_flow.apply_divergence_nn_LR with its CPU-built mesh moved to the device."""
+    def one(shift):
+        cc, dd = (torch.flip(c, (3,)), torch.flip(d, (3,))) if shift > 0 else (c, d)
+        delta = orf.row_flow_delta(sdc, orf.make_input(dd, div, conv))
+        z = orf.warp_delta(cc.cpu(), delta.cpu(), dd.shape[3])
+        return torch.flip(z, (3,)) if shift > 0 else z
+    return one(-1), one(1)
+
+
 def test_row_flow_delta_golden():
     from nunif_b200.iw3 import RowFlowV3
     g = load_golden("row_flow")
@@ -69,9 +79,12 @@ def test_row_flow_1080p_runs_and_matches_oracle_amp():
     c = synth.synth_image(31, 3, 1080, 1920).unsqueeze(0).to(DEV)
     d = synth.synth_depth(32, 1, 392, 686).to(DEV)
     l, r = apply_divergence_nn_LR(m, c, d, 2.0, 0.5)
+    # the fp32 oracle evaluated on the GPU by torch (a 1080p frame through it takes minutes on the CPU)
     sdc = {k: v.to(DEV) for k, v in sd.items()}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     with torch.no_grad():
-        lo, ro = orf.apply_divergence_nn_LR({k: v.cpu() for k, v in sdc.items()}, c.cpu(), d.cpu(), 2.0, 0.5)
+        lo, ro = _oracle_lr_on_device(sdc, c, d, 2.0, 0.5)
     sl, sr = stats(l, lo), stats(r, ro)
     log_metric("row_flow_1080p", left_max=sl["max"], right_max=sr["max"], left_mean=sl["mean"], right_mean=sr["mean"])
     assert sl["mean"] < 1e-3 and sr["mean"] < 1e-3
