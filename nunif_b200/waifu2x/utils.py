@@ -55,88 +55,65 @@ class Waifu2x():
     def has_model_file(self, filename):
         return path.exists(path.join(self.model_dir, filename))
 
-    def _load_model(self, method, noise_level):
-        """waifu2x/utils.py:128-176."""
-        if method == "scale4x":
-            if self.scale4x_model is not None:
-                return
-            if self.has_model_file("scale4x.pth"):
-                self.scale4x_model = self.load_model_by_name("scale4x.pth")
-            else:
-                raise FileNotFoundError(f"scale4x.pth not found in {self.model_dir}")
-        elif method == "scale":
-            if self.scale_model is not None:
-                return
-            if self.has_model_file("scale2x.pth"):
-                self.scale_model = self.load_model_by_name("scale2x.pth")
-            else:
-                if self.scale4x_model is None:
-                    self._load_model("scale4x", noise_level)
-                self.scale_model = self.scale4x_model.to_2x()
-        elif method == "noise_scale4x":
-            if self.noise_scale4x_models[noise_level] is not None:
-                return
-            if self.has_model_file(f"noise{noise_level}_scale4x.pth"):
-                self.noise_scale4x_models[noise_level] = self.load_model_by_name(f"noise{noise_level}_scale4x.pth")
-            else:
-                raise FileNotFoundError(f"noise{noise_level}_scale4x.pth not found in {self.model_dir}")
-        elif method == "noise_scale":
-            if self.noise_scale_models[noise_level] is not None:
-                return
-            if self.has_model_file(f"noise{noise_level}_scale2x.pth"):
-                self.noise_scale_models[noise_level] = self.load_model_by_name(f"noise{noise_level}_scale2x.pth")
-            else:
-                if self.noise_scale4x_models[noise_level] is None:
-                    self._load_model("noise_scale4x", noise_level)
-                self.noise_scale_models[noise_level] = self.noise_scale4x_models[noise_level].to_2x()
-        elif method == "noise":
-            if self.noise_models[noise_level] is not None:
-                return
-            if self.has_model_file(f"noise{noise_level}.pth"):
-                self.noise_models[noise_level] = self.load_model_by_name(f"noise{noise_level}.pth")
-            else:
-                if self.noise_scale4x_models[noise_level] is None:
-                    self._load_model("noise_scale4x", noise_level)
-                self.noise_models[noise_level] = self.noise_scale4x_models[noise_level].to_1x()
+    # method -> (checkpoint file pattern, method whose 4x model the 2x/1x variant is derived from, derivation)
+    # (waifu2x/utils.py:128-176: the released swin_unet directories only ship 4x checkpoints; 2x and 1x are the
+    #  4x network followed by an antialiased bicubic downscale, swin_unet.py:289-303)
+    _CHECKPOINTS = {
+        "scale4x": ("scale4x.pth", None, None),
+        "scale": ("scale2x.pth", "scale4x", "to_2x"),
+        "noise_scale4x": ("noise{n}_scale4x.pth", None, None),
+        "noise_scale": ("noise{n}_scale2x.pth", "noise_scale4x", "to_2x"),
+        "noise": ("noise{n}.pth", "noise_scale4x", "to_1x"),
+    }
+
+    def _slot(self, method, noise_level, value=None):
+        per_level = {"noise": self.noise_models, "noise_scale": self.noise_scale_models,
+                     "noise_scale4x": self.noise_scale4x_models}.get(method)
+        if value is None:
+            return per_level[noise_level] if per_level is not None else getattr(self, method + "_model")
+        if per_level is not None:
+            per_level[noise_level] = value
         else:
+            setattr(self, method + "_model", value)
+        return value
+
+    def _load_model(self, method, noise_level):
+        """waifu2x/utils.py:128-176, table-driven."""
+        if method not in self._CHECKPOINTS:
             raise ValueError(method)
+        if self._slot(method, noise_level) is not None:
+            return
+        pattern, base, derive = self._CHECKPOINTS[method]
+        filename = pattern.format(n=noise_level)
+        if self.has_model_file(filename):
+            self._slot(method, noise_level, self.load_model_by_name(filename))
+        elif base is None:
+            raise FileNotFoundError(f"{filename} not found in {self.model_dir}")
+        else:
+            self._load_model(base, noise_level)
+            self._slot(method, noise_level, getattr(self._slot(base, noise_level), derive)())
 
     def load_model(self, method, noise_level):
-        """waifu2x/utils.py:178-199."""
+        """waifu2x/utils.py:178-199: also keeps the plain scale model next to a noise_scale one (alpha channel pass)."""
         assert (method in ("scale", "noise_scale", "noise", "scale4x", "noise_scale4x"))
         assert (method in {"scale", "scale4x"} or 0 <= noise_level and noise_level < 4)
-        if method in {"scale", "scale4x", "noise"}:
-            self._load_model(method, noise_level)
-        elif method == "noise_scale4x":
-            self._load_model(method, noise_level)
+        self._load_model(method, noise_level)
+        companion = {"noise_scale4x": "scale4x", "noise_scale": "scale"}.get(method)
+        if companion is not None:
             try:
-                self._load_model("scale4x", -1)
-            except FileNotFoundError:
-                pass
-        elif method == "noise_scale":
-            self._load_model(method, noise_level)
-            try:
-                self._load_model("scale", -1)
+                self._load_model(companion, -1)
             except FileNotFoundError:
                 pass
 
     def load_model_all(self, load_4x=True):
         """waifu2x/utils.py:201-216."""
-        if load_4x:
-            self._load_model("scale4x", -1)
-            for noise_level in range(4):
-                self._load_model("noise_scale4x", noise_level)
-        self._load_model("scale", -1)
-        for noise_level in range(4):
-            self._load_model("noise_scale", noise_level)
-        for noise_level in range(4):
-            self._load_model("noise", noise_level)
+        order = (["scale4x", "noise_scale4x"] if load_4x else []) + ["scale", "noise_scale", "noise"]
+        for method in order:
+            for noise_level in ([-1] if method in {"scale", "scale4x"} else range(4)):
+                self._load_model(method, noise_level)
 
     def _model(self, method, noise_level):
-        return {"scale": lambda: self.scale_model, "scale4x": lambda: self.scale4x_model,
-                "noise": lambda: self.noise_models[noise_level],
-                "noise_scale": lambda: self.noise_scale_models[noise_level],
-                "noise_scale4x": lambda: self.noise_scale4x_models[noise_level]}[method]()
+        return self._slot(method, noise_level)
 
     @torch.inference_mode()
     def render(self, x, method, noise_level, tile_size=None, batch_size=None, enable_amp=False):
