@@ -56,7 +56,8 @@ def test_hub_image_model(model_dir):
     assert rgb.shape == (3, 192, 256) and alpha is None
     im = m.infer(x)                                  # PIL out
     assert im.size == (256, 192) and im.mode == "RGB"
-    assert m.infer(im, method="noise_scale4x", noise_level=1, output_type="tensor")[0].shape == (3, 768, 1024)
+    n = waifu2x("art", method="scale4x", noise_level=1, model_dir=model_dir, tile_size=64, batch_size=4)   # -> noise_scale4x (hub.py:151-163)
+    assert n.method == "noise_scale4x" and n.infer(im, output_type="tensor")[0].shape == (3, 768, 1024)
     c = waifu2x("cunet/art", method="scale", model_dir=model_dir, tile_size=64, batch_size=4)
     assert c.infer(x, output_type="tensor")[0].shape == (3, 96, 128)
     with pytest.raises(ValueError):
