@@ -83,7 +83,9 @@ enum {
     /* Depth-Anything-V2 ViT-S: third-party net the reference loads through torch.hub
      * (iw3/depth_anything_model.py:223-230); state_dict keys `pretrained.*`, `depth_head.*` */
     NB200_MODEL_DEPTH_ANYTHING_V2_S = 6,
-    NB200_MODEL_ROW_FLOW_V3 = 7     /* sbs.row_flow_v3, iw3's default learned stereo warp (iw3/models/row_flow_v3.py) */
+    NB200_MODEL_ROW_FLOW_V3 = 7,    /* sbs.row_flow_v3, iw3's default learned stereo warp (iw3/models/row_flow_v3.py) */
+    NB200_MODEL_DEPTH_ANYTHING_V2_B = 8,   /* Any_V2_B: ViT-B encoder, 128 head features */
+    NB200_MODEL_DEPTH_ANYTHING_V2_L = 9    /* Any_V2_L: ViT-L encoder (24 blocks), 256 head features */
 };
 
 /* Create a model from named fp32 host tensors using the reference's state_dict

@@ -19,6 +19,7 @@ struct DaRefineW {
 };
 struct DaW {
     int dim = 384, depth = 12, heads = 6, feat = 64, kpad = 640, pos_grid = 37;
+    int c0pad = 64;    // channel stride of the first reassembled map (oc[0] rounded up to a multiple of 32)
     int oc[4] = {48, 96, 192, 384}, idx[4] = {2, 5, 8, 11};
     Lin patch, reasm[4], resize3, rn[4], oc1, oc2;
     DaRefineW ref[4];   // refinenet1..4
@@ -99,9 +100,20 @@ static Lin pack_conv_nobias(Packer& pk, const std::string& name, int cout, int c
     return l;
 }
 
-static std::shared_ptr<DaW> pack_depth_anything(Packer& pk) {
+// encoder: 0 = ViT-S, 1 = ViT-B, 2 = ViT-L (Depth-Anything-V2 dpt.py model_configs / intermediate_layer_idx)
+static std::shared_ptr<DaW> pack_depth_anything(Packer& pk, int encoder) {
     auto d = std::make_shared<DaW>();
     DaW& w = *d;
+    if (encoder == 1) {
+        w.dim = 768; w.depth = 12; w.heads = 12; w.feat = 128;
+        const int oc[4] = {96, 192, 384, 768};
+        for (int i = 0; i < 4; ++i) w.oc[i] = oc[i];
+    } else if (encoder == 2) {
+        w.dim = 1024; w.depth = 24; w.heads = 16; w.feat = 256;
+        const int oc[4] = {256, 512, 1024, 1024}, idx[4] = {4, 11, 17, 23};
+        for (int i = 0; i < 4; ++i) { w.oc[i] = oc[i]; w.idx[i] = idx[i]; }
+    }
+    w.c0pad = (w.oc[0] + 31) / 32 * 32;
     const int dim = w.dim;
     {   // patch embedding: Conv2d(3, dim, 14, 14) as a Linear over im2col rows, K = 588 zero-padded to 640
         Lin l;
@@ -154,7 +166,7 @@ static std::shared_ptr<DaW> pack_depth_anything(Packer& pk) {
     w.reasm[3] = pack_conv(pk, h + "projects.3", w.oc[3], dim, 1, 1);
     w.resize3 = pack_conv(pk, h + "resize_layers.3", w.oc[3], w.oc[3], 3, 3);
     for (int i = 0; i < 4; ++i)
-        w.rn[i] = pack_conv_nobias(pk, h + "scratch.layer" + std::to_string(i + 1) + "_rn", w.feat, w.oc[i], i == 0 ? 64 : w.oc[i]);
+        w.rn[i] = pack_conv_nobias(pk, h + "scratch.layer" + std::to_string(i + 1) + "_rn", w.feat, w.oc[i], i == 0 ? w.c0pad : w.oc[i]);
     for (int r = 0; r < 4; ++r) {
         const std::string p = h + "scratch.refinenet" + std::to_string(r + 1) + ".";
         w.ref[r].out_conv = pack_conv(pk, p + "out_conv", w.feat, w.feat, 1, 1);
@@ -231,9 +243,8 @@ static int da_conv(cudaStream_t st, const nb200_model* m, const Lin& l, const __
 }
 
 // FeatureFusionBlock (dpt blocks.py): x0 (+ resConfUnit1(x1)) -> resConfUnit2 -> bilinear resize -> out_conv
-static int da_fusion(cudaStream_t st, const nb200_model* m, const DaRefineW& r, const __half* x0, const __half* x1, int B, int h, int w,
+static int da_fusion(cudaStream_t st, const nb200_model* m, const DaRefineW& r, int F, const __half* x0, const __half* x1, int B, int h, int w,
                      int oh, int ow, __half* t_relu, __half* t_c1, __half* t_sum, __half* t_u, __half* t_up, __half* out) {
-    const int F = 64;
     const long long n = (long long)B * h * w * F;
     const __half* cur = x0;
     if (x1) {
@@ -254,7 +265,8 @@ static int da_fusion(cudaStream_t st, const nb200_model* m, const DaRefineW& r, 
 static int depth_anything_forward(nb200_model* m, cudaStream_t st, const float* x, int B, int H, int W, float* depth) {
     DaW& w = *m->da;
     NB_CHECK(H % 14 == 0 && W % 14 == 0 && H >= 14 && W >= 14, "input height and width must be multiples of 14 (batch_preprocess)");
-    const int dim = w.dim, ph = H / 14, pw = W / 14, P = ph * pw, N = P + 1;
+    const int dim = w.dim, ph = H / 14, pw = W / 14, P = ph * pw, N = P + 1, F = w.feat, F2 = w.feat / 2;
+    const int c0 = w.oc[0], c0p = w.c0pad, c1 = w.oc[1], c2 = w.oc[2], c3 = w.oc[3];
     const long long M = (long long)B * N;
     if (w.pos_ph != ph || w.pos_pw != pw) {
         std::vector<float> tab;
@@ -271,49 +283,50 @@ static int depth_anything_forward(nb200_model* m, cudaStream_t st, const float* 
     // ---- workspace
     size_t bytes = 4096;
     auto need = [&](size_t elems, size_t esz) { bytes += ((elems * esz + 255) & ~(size_t)255) + 256; };
-    need((size_t)B * P * w.kpad, 2); need((size_t)B * P * 768, 2); need((size_t)M * dim, 4); need((size_t)M * dim, 2);
+    const size_t tcols = (size_t)16 * c0 > (size_t)dim ? (size_t)16 * c0 : (size_t)dim;
+    need((size_t)B * P * w.kpad, 2); need((size_t)B * P * tcols, 2); need((size_t)M * dim, 4); need((size_t)M * dim, 2);
     need((size_t)M * 3 * dim, 2); need((size_t)M * dim, 2); need((size_t)M * 4 * dim, 2); need((size_t)M * dim, 2);
     for (int i = 0; i < 4; ++i) need((size_t)M * dim, 2);
-    need((size_t)B * h1 * w1 * 64, 2); need((size_t)B * h2 * w2 * 96, 2); need((size_t)B * h3 * w3 * 192, 2); need((size_t)B * h3 * w3 * 384, 2);
-    need((size_t)B * h4 * w4 * 3456, 2); need((size_t)B * h4 * w4 * 384, 2);
-    need((size_t)B * h1 * w1 * 64, 2); need((size_t)B * h2 * w2 * 64, 2); need((size_t)B * h3 * w3 * 64, 2); need((size_t)B * h4 * w4 * 64, 2);
-    for (int i = 0; i < 4; ++i) need((size_t)B * h1 * w1 * 64, 2);          // relu / conv1 / sum / unit out (largest fusion resolution)
-    need((size_t)B * hp * wp * 64, 2);                                       // upsampled
-    need((size_t)B * h3 * w3 * 64, 2); need((size_t)B * h2 * w2 * 64, 2); need((size_t)B * h1 * w1 * 64, 2); need((size_t)B * hp * wp * 64, 2);  // paths
-    need((size_t)B * hp * wp * 32, 2); need((size_t)B * H * W * 32, 2); need((size_t)B * H * W * 32, 2);
+    need((size_t)B * h1 * w1 * c0p, 2); need((size_t)B * h2 * w2 * c1, 2); need((size_t)B * h3 * w3 * c2, 2); need((size_t)B * h3 * w3 * c3, 2);
+    need((size_t)B * h4 * w4 * 9 * c3, 2); need((size_t)B * h4 * w4 * c3, 2);
+    need((size_t)B * h1 * w1 * F, 2); need((size_t)B * h2 * w2 * F, 2); need((size_t)B * h3 * w3 * F, 2); need((size_t)B * h4 * w4 * F, 2);
+    for (int i = 0; i < 4; ++i) need((size_t)B * h1 * w1 * F, 2);           // relu / conv1 / sum / unit out (largest fusion resolution)
+    need((size_t)B * hp * wp * F, 2);                                        // upsampled
+    need((size_t)B * h3 * w3 * F, 2); need((size_t)B * h2 * w2 * F, 2); need((size_t)B * h1 * w1 * F, 2); need((size_t)B * hp * wp * F, 2);  // paths
+    need((size_t)B * hp * wp * F2, 2); need((size_t)B * H * W * F2, 2); need((size_t)B * H * W * 32, 2);
     if (m->ensure_ws(bytes)) return 1;
     Arena a{m->ws, 0, m->ws_bytes};
     __half* Apatch = a.take<__half>((size_t)B * P * w.kpad);
-    __half* T = a.take<__half>((size_t)B * P * 768);     // patch GEMM output, later the reassemble-0 GEMM output
+    __half* T = a.take<__half>((size_t)B * P * tcols);   // patch GEMM output, later the reassemble-0 GEMM output
     float* X32 = a.take<float>((size_t)M * dim);
     __half* Hn = a.take<__half>((size_t)M * dim);
     __half* QKV = a.take<__half>((size_t)M * 3 * dim);
     __half* ATT = a.take<__half>((size_t)M * dim);
     __half* HID = a.take<__half>((size_t)M * 4 * dim);
     __half* D = a.take<__half>((size_t)M * dim);
-    __half* F[4];
-    for (int i = 0; i < 4; ++i) F[i] = a.take<__half>((size_t)M * dim);
-    __half* L1 = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* L2 = a.take<__half>((size_t)B * h2 * w2 * 96);
-    __half* L3 = a.take<__half>((size_t)B * h3 * w3 * 192);
-    __half* L4lin = a.take<__half>((size_t)B * h3 * w3 * 384);
-    __half* L4col = a.take<__half>((size_t)B * h4 * w4 * 3456);
-    __half* L4 = a.take<__half>((size_t)B * h4 * w4 * 384);
-    __half* R1 = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* R2 = a.take<__half>((size_t)B * h2 * w2 * 64);
-    __half* R3 = a.take<__half>((size_t)B * h3 * w3 * 64);
-    __half* R4 = a.take<__half>((size_t)B * h4 * w4 * 64);
-    __half* t_relu = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* t_c1 = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* t_sum = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* t_u = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* t_up = a.take<__half>((size_t)B * hp * wp * 64);
-    __half* P4 = a.take<__half>((size_t)B * h3 * w3 * 64);
-    __half* P3 = a.take<__half>((size_t)B * h2 * w2 * 64);
-    __half* P2 = a.take<__half>((size_t)B * h1 * w1 * 64);
-    __half* P1 = a.take<__half>((size_t)B * hp * wp * 64);
-    __half* O1 = a.take<__half>((size_t)B * hp * wp * 32);
-    __half* O1u = a.take<__half>((size_t)B * H * W * 32);
+    __half* FE[4];
+    for (int i = 0; i < 4; ++i) FE[i] = a.take<__half>((size_t)M * dim);
+    __half* L1 = a.take<__half>((size_t)B * h1 * w1 * c0p);
+    __half* L2 = a.take<__half>((size_t)B * h2 * w2 * c1);
+    __half* L3 = a.take<__half>((size_t)B * h3 * w3 * c2);
+    __half* L4lin = a.take<__half>((size_t)B * h3 * w3 * c3);
+    __half* L4col = a.take<__half>((size_t)B * h4 * w4 * 9 * c3);
+    __half* L4 = a.take<__half>((size_t)B * h4 * w4 * c3);
+    __half* R1 = a.take<__half>((size_t)B * h1 * w1 * F);
+    __half* R2 = a.take<__half>((size_t)B * h2 * w2 * F);
+    __half* R3 = a.take<__half>((size_t)B * h3 * w3 * F);
+    __half* R4 = a.take<__half>((size_t)B * h4 * w4 * F);
+    __half* t_relu = a.take<__half>((size_t)B * h1 * w1 * F);
+    __half* t_c1 = a.take<__half>((size_t)B * h1 * w1 * F);
+    __half* t_sum = a.take<__half>((size_t)B * h1 * w1 * F);
+    __half* t_u = a.take<__half>((size_t)B * h1 * w1 * F);
+    __half* t_up = a.take<__half>((size_t)B * hp * wp * F);
+    __half* P4 = a.take<__half>((size_t)B * h3 * w3 * F);
+    __half* P3 = a.take<__half>((size_t)B * h2 * w2 * F);
+    __half* P2 = a.take<__half>((size_t)B * h1 * w1 * F);
+    __half* P1 = a.take<__half>((size_t)B * hp * wp * F);
+    __half* O1 = a.take<__half>((size_t)B * hp * wp * F2);
+    __half* O1u = a.take<__half>((size_t)B * H * W * F2);
     __half* O2 = a.take<__half>((size_t)B * H * W * 32);
 
     // ---- encoder (dinov2 vision_transformer.py prepare_tokens_with_masks + blocks)
@@ -334,7 +347,7 @@ static int depth_anything_forward(nb200_model* m, cudaStream_t st, const float* 
         pending = D;
         if (nf < 4 && i == w.idx[nf]) {
             // get_intermediate_layers(..., norm=True): the final LayerNorm applied to this block's output
-            if (da_add_layernorm(st, X32, D, m->at<float>(w.normw), m->at<float>(w.normb), F[nf], M, dim)) return 1;
+            if (da_add_layernorm(st, X32, D, m->at<float>(w.normw), m->at<float>(w.normb), FE[nf], M, dim)) return 1;
             pending = nullptr;
             ++nf;
         }
@@ -342,30 +355,30 @@ static int depth_anything_forward(nb200_model* m, cudaStream_t st, const float* 
     // ---- DPT head (dpt.py DPTHead.forward); the class token row of every image is skipped by the A view
     auto reassemble = [&](int i, __half* out, int out_mode, int cout) {
         ConvGemm g;
-        g.A = F[i] + dim; g.B = B; g.Hi = ph; g.Wi = pw; g.Ci = dim; g.Cin = dim; g.kind = CG_LINEAR_2D;
+        g.A = FE[i] + dim; g.B = B; g.Hi = ph; g.Wi = pw; g.Ci = dim; g.Cin = dim; g.kind = CG_LINEAR_2D;
         g.a_row_stride = (long long)pw * dim; g.a_img_stride = (long long)N * dim;
         g.Wt = m->at<__half>(w.reasm[i].w); g.N = w.reasm[i].N; g.bias = m->at<float>(w.reasm[i].b); g.act = ACT_NONE;
         g.out = out; g.ldo = out_mode == OUT_PIXSHUF2 ? cout : w.reasm[i].N; g.out_mode = out_mode; g.cout = cout;
         return conv_gemm(st, g);
     };
     if (reassemble(0, T, 0, 0)) return 1;                                   // [B*P][16*48]
-    if (da_depth_to_space4(st, T, B, ph, pw, 48, L1, 64)) return 1;         // [B][4ph][4pw][48 -> 64]
-    if (reassemble(1, L2, OUT_PIXSHUF2, 96)) return 1;                      // [B][2ph][2pw][96]
+    if (da_depth_to_space4(st, T, B, ph, pw, c0, L1, c0p)) return 1;        // [B][4ph][4pw][c0 -> c0p]
+    if (reassemble(1, L2, OUT_PIXSHUF2, c1)) return 1;                      // [B][2ph][2pw][c1]
     if (reassemble(2, L3, 0, 0)) return 1;
     if (reassemble(3, L4lin, 0, 0)) return 1;
-    if (da_im2col_s2(st, L4lin, B, h3, w3, 384, L4col)) return 1;
-    if (da_linear(st, m, w.resize3, L4col, (long long)B * h4 * w4, 3456, L4, ACT_NONE)) return 1;
-    if (da_conv(st, m, w.rn[0], L1, B, h1, w1, 64, 64, R1, ACT_NONE, nullptr, true)) return 1;
-    if (da_conv(st, m, w.rn[1], L2, B, h2, w2, 96, 96, R2, ACT_NONE, nullptr, true)) return 1;
-    if (da_conv(st, m, w.rn[2], L3, B, h3, w3, 192, 192, R3, ACT_NONE, nullptr, true)) return 1;
-    if (da_conv(st, m, w.rn[3], L4, B, h4, w4, 384, 384, R4, ACT_NONE, nullptr, true)) return 1;
-    if (da_fusion(st, m, w.ref[3], R4, nullptr, B, h4, w4, h3, w3, t_relu, t_c1, t_sum, t_u, t_up, P4)) return 1;
-    if (da_fusion(st, m, w.ref[2], P4, R3, B, h3, w3, h2, w2, t_relu, t_c1, t_sum, t_u, t_up, P3)) return 1;
-    if (da_fusion(st, m, w.ref[1], P3, R2, B, h2, w2, h1, w1, t_relu, t_c1, t_sum, t_u, t_up, P2)) return 1;
-    if (da_fusion(st, m, w.ref[0], P2, R1, B, h1, w1, hp, wp, t_relu, t_c1, t_sum, t_u, t_up, P1)) return 1;
-    if (da_conv(st, m, w.oc1, P1, B, hp, wp, 64, 64, O1, ACT_NONE, nullptr, true)) return 1;
-    if (da_upsample_bilinear(st, O1, B, hp, wp, 32, O1u, H, W)) return 1;
-    if (da_conv(st, m, w.oc2, O1u, B, H, W, 32, 32, O2, ACT_RELU, nullptr, true)) return 1;
+    if (da_im2col_s2(st, L4lin, B, h3, w3, c3, L4col)) return 1;
+    if (da_linear(st, m, w.resize3, L4col, (long long)B * h4 * w4, 9 * c3, L4, ACT_NONE)) return 1;
+    if (da_conv(st, m, w.rn[0], L1, B, h1, w1, c0p, c0p, R1, ACT_NONE, nullptr, true)) return 1;
+    if (da_conv(st, m, w.rn[1], L2, B, h2, w2, c1, c1, R2, ACT_NONE, nullptr, true)) return 1;
+    if (da_conv(st, m, w.rn[2], L3, B, h3, w3, c2, c2, R3, ACT_NONE, nullptr, true)) return 1;
+    if (da_conv(st, m, w.rn[3], L4, B, h4, w4, c3, c3, R4, ACT_NONE, nullptr, true)) return 1;
+    if (da_fusion(st, m, w.ref[3], F, R4, nullptr, B, h4, w4, h3, w3, t_relu, t_c1, t_sum, t_u, t_up, P4)) return 1;
+    if (da_fusion(st, m, w.ref[2], F, P4, R3, B, h3, w3, h2, w2, t_relu, t_c1, t_sum, t_u, t_up, P3)) return 1;
+    if (da_fusion(st, m, w.ref[1], F, P3, R2, B, h2, w2, h1, w1, t_relu, t_c1, t_sum, t_u, t_up, P2)) return 1;
+    if (da_fusion(st, m, w.ref[0], F, P2, R1, B, h1, w1, hp, wp, t_relu, t_c1, t_sum, t_u, t_up, P1)) return 1;
+    if (da_conv(st, m, w.oc1, P1, B, hp, wp, F, F, O1, ACT_NONE, nullptr, true)) return 1;
+    if (da_upsample_bilinear(st, O1, B, hp, wp, F2, O1u, H, W)) return 1;
+    if (da_conv(st, m, w.oc2, O1u, B, H, W, F2, F2, O2, ACT_RELU, nullptr, true)) return 1;
     return da_head_final(st, O2, (long long)B * H * W, 32, m->at<float>(w.oc3w), w.oc3b, depth);
 }
 

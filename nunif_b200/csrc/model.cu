@@ -438,7 +438,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
                                   const int64_t* numel, int no_clip, nb200_model** out) {
     NB_CHECK(out && names && data && numel, "null pointer");
-    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_ROW_FLOW_V3, "unknown model kind");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_DEPTH_ANYTHING_V2_L, "unknown model kind");
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
@@ -463,7 +463,9 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
         case NB200_MODEL_SWIN_UNET_4X: pack_swin(pk, m->sw, 4); m->scale = 4; m->offset = 32; m->blend = 16; break;  // :267
         case NB200_MODEL_UPCUNET: m->cu = pack_cunet(pk, true); m->scale = 2; m->offset = 36; m->blend = 0; break;   // cunet.py:144
         case NB200_MODEL_CUNET: m->cu = pack_cunet(pk, false); m->scale = 1; m->offset = 28; m->blend = 0; break;    // cunet.py:178
-        case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk); m->scale = 1; break;
+        case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk, 0); m->scale = 1; break;
+        case NB200_MODEL_DEPTH_ANYTHING_V2_B: m->da = pack_depth_anything(pk, 1); m->scale = 1; break;
+        case NB200_MODEL_DEPTH_ANYTHING_V2_L: m->da = pack_depth_anything(pk, 2); m->scale = 1; break;
         case NB200_MODEL_ROW_FLOW_V3: m->rf = pack_row_flow(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;   // row_flow_v3.py:37
     }
     if (pk.err.empty())
@@ -625,7 +627,7 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
 // DepthAnythingV2.forward (what DepthAnythingModel._forward calls, iw3/depth_anything_model.py:113-119)
 extern "C" int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth, void* stream) {
     NB_CHECK(m && x && depth, "null pointer");
-    NB_CHECK(m->kind == NB200_MODEL_DEPTH_ANYTHING_V2_S && m->da, "model is not a Depth-Anything network");
+    NB_CHECK(m->da, "model is not a Depth-Anything network");
     NB_CHECK(B > 0, "empty batch");
     return depth_anything_forward(m, (cudaStream_t)stream, x, B, H, W, depth);
 }

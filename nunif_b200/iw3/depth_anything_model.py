@@ -13,13 +13,18 @@ from .. import _lib
 from .depth_anything_preprocess import batch_preprocess
 from .dilation import dilate_edge, edge_dilation_is_enabled
 
-KIND_DEPTH_ANYTHING_V2_S = 6     # NB200_MODEL_DEPTH_ANYTHING_V2_S
+# NB200_MODEL_DEPTH_ANYTHING_V2_{S,B,L}; model types as in iw3/depth_anything_model.py NAME_MAP
+KINDS = {"vits": 6, "vitb": 8, "vitl": 9}
+ENCODER_OF = {"Any_V2_S": "vits", "Any_V2_B": "vitb", "Any_V2_L": "vitl"}
 
 
 class DepthAnythingNet:
     """The packed network: ``net(x)`` == ``DepthAnythingV2.forward`` (x: B,3,H,W normalised, H,W % 14 == 0 -> B,H,W)."""
 
-    def __init__(self, state_dict, device="cuda:0"):
+    def __init__(self, state_dict, device="cuda:0", encoder="vits"):
+        if encoder not in KINDS:
+            raise ValueError(f"encoder: choose from {list(KINDS)}")
+        self.encoder = encoder
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("nunif_b200 models live on a CUDA (sm_100) device; there is no CPU path")
@@ -30,7 +35,7 @@ class DepthAnythingNet:
         numels = (ctypes.c_int64 * n)(*[v.numel() for _, v in items])
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().nb200_model_create(KIND_DEPTH_ANYTHING_V2_S, n, names, datas, numels, 0, ctypes.byref(h)))
+            _lib.check(_lib.lib().nb200_model_create(KINDS[encoder], n, names, datas, numels, 0, ctypes.byref(h)))
         self._h = h
         self.metric_depth = False
         self.prep_lower_bound = 392
@@ -88,8 +93,8 @@ class DepthAnythingModel:
     """BaseDepthModel-shaped wrapper (iw3/base_depth_model.py) around a DepthAnythingNet."""
 
     def __init__(self, model_type="Any_V2_S"):
-        if model_type != "Any_V2_S":
-            raise ValueError("the B200 engine implements Any_V2_S (Depth-Anything-V2 ViT-S)")
+        if model_type not in ENCODER_OF:
+            raise ValueError(f"the B200 engine implements {list(ENCODER_OF)} (Depth-Anything-V2 relative-depth models)")
         self.model_type = model_type
         self.model = None
         self.device = None
@@ -99,7 +104,7 @@ class DepthAnythingModel:
         """The reference downloads the checkpoint through torch.hub (depth_anything_model.py:223-230); here the caller
         passes the same state_dict (e.g. torch.load of depth_anything_v2_vits.pth)."""
         self.device = torch.device(f"cuda:{gpu}") if isinstance(gpu, int) else torch.device(gpu)
-        self.model = DepthAnythingNet(state_dict, self.device)
+        self.model = DepthAnythingNet(state_dict, self.device, encoder=ENCODER_OF[self.model_type])
         lb = resolution or 392                                        # :232-235
         if lb % 14 != 0:
             lb += 14 - lb % 14

@@ -200,7 +200,8 @@ def depth_anything_v2_state_dict(seed=0, encoder="vits", pos_grid=37):
     No checkpoint can be downloaded here; gains are chosen so that activations stay O(1) through the 12 blocks and the
     predicted depth is a non-trivial positive map.  pos_grid=37 is the 518/14 training grid of the released models."""
     dim, depth, heads, feat, oc = {"vits": (384, 12, 6, 64, (48, 96, 192, 384)),
-                                   "vitb": (768, 12, 12, 128, (96, 192, 384, 768))}[encoder]
+                                   "vitb": (768, 12, 12, 128, (96, 192, 384, 768)),
+                                   "vitl": (1024, 24, 16, 256, (256, 512, 1024, 1024))}[encoder]
     g = torch.Generator().manual_seed(10_000 + seed)
 
     def rn(*shape, std=1.0):

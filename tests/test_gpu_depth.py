@@ -76,3 +76,18 @@ def test_pos_table_interpolation_matches_oracle():
     got = DepthAnythingNet(sd, DEV)(x.to(DEV)).cpu()
     ref32, refamp = _refs(sd, x)
     _check("depth_anything_pos_only", got, ref32, refamp)
+
+
+@pytest.mark.parametrize("encoder,H,W", [("vitb", 14 * 6, 14 * 9), ("vitl", 14 * 5, 14 * 7)])
+def test_depth_anything_base_and_large_encoders(encoder, H, W):
+    """Any_V2_B / Any_V2_L share the code path; only the table in depth_model.inl changes (dim, heads, depth, head widths)."""
+    from nunif_b200.iw3 import DepthAnythingNet
+    sd = synth.depth_anything_v2_state_dict(5, encoder=encoder, pos_grid=8)
+    x = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(H * W))
+    got = DepthAnythingNet(sd, DEV, encoder=encoder)(x.to(DEV)).cpu()
+    sdc = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad():
+        ref32 = oda.depth_anything_forward(sdc, x.to(DEV).float(), encoder).cpu()
+        with torch.autocast("cuda", dtype=torch.float16):
+            refamp = oda.depth_anything_forward(sdc, x.to(DEV), encoder).float().cpu()
+    _check(f"depth_anything_{encoder}", got, ref32, refamp)
