@@ -392,9 +392,16 @@ def run_b200(args):
         prof = json.loads(buf.value.decode())
         del y
 
-        iw3 = bench_iw3(dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if rank == 0 else None
-        upc = bench_upcunet(dev, lib, x) if rank == 0 else None
-        cfg4 = bench_8k_downscaled(dev, model) if rank == 0 else None
+        # secondary objects (rank 0 only): never allowed to take the headline line down with them
+        def guarded(fn, *a, **k):
+            try:
+                return fn(*a, **k)
+            except Exception as e:  # noqa: BLE001
+                torch.cuda.synchronize()
+                return {"error": f"{type(e).__name__}: {e}"}
+        iw3 = guarded(bench_iw3, dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if rank == 0 else None
+        upc = guarded(bench_upcunet, dev, lib, x) if rank == 0 else None
+        cfg4 = guarded(bench_8k_downscaled, dev, model) if rank == 0 else None
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
