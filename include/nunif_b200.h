@@ -248,6 +248,16 @@ int nb200_zoe_preprocess_size(int H, int W, int h_height, int v_height, int mod,
 int nb200_zoe_preprocess(const float* x, int B, int H, int W, int frame_h, int frame_w, int pad_h,
                          int pad_w, float* out, void* stream);
 
+/* iw3/anaglyph.py:95-110 apply_anaglyph_redcyan: l, r [B][3][H][W] fp32 -> out [B][3][H][W]. */
+enum { NB200_ANAGLYPH_DUBOIS = 0, NB200_ANAGLYPH_DUBOIS2 = 1, NB200_ANAGLYPH_COLOR = 2, NB200_ANAGLYPH_GRAY = 3,
+       NB200_ANAGLYPH_HALF_COLOR = 4, NB200_ANAGLYPH_WIMMER = 5, NB200_ANAGLYPH_WIMMER2 = 6 };
+int nb200_anaglyph(const float* l, const float* r, int B, int H, int W, int type, float* out, void* stream);
+
+/* TF.resize(x, (oh, ow), BICUBIC, antialias=True) on `planes` fp32 H x W planes (half-SBS / half-TB and the
+ * max-output-size resize of postprocess_image, iw3/utils.py:445-485); clamp01_out applies the following clamp. */
+int nb200_resize_bicubic_aa(const float* x, int planes, int H, int W, int oh, int ow, int clamp01_out,
+                            float* out, void* stream);
+
 /* Kernel-class device timing (CUDA events around every launch of this library) used by
  * bench.py for the live roofline figure.  report writes a JSON object
  * {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...} and synchronises the device. */

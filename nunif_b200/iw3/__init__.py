@@ -17,3 +17,4 @@ from .depth_anything_preprocess import batch_preprocess, preprocess_size  # noqa
 from .depth_anything_model import DepthAnythingModel, DepthAnythingNet, batch_infer  # noqa: F401
 from . import zoedepth_preprocess  # noqa: F401
 from .row_flow import RowFlowV3, apply_divergence_nn_LR, apply_divergence_nn_delta  # noqa: F401
+from .postprocess import postprocess_image, postprocess_padding, resize_bicubic_aa  # noqa: F401

@@ -266,9 +266,49 @@ def gen_row_flow():
     save("row_flow", **out)
 
 
+POSTPROCESS_CASES = [
+    ("sbs", {}),
+    ("half_sbs", {"half_sbs": True}),
+    ("half_tb", {"half_tb": True}),
+    ("tb", {"tb": True}),
+    ("cross", {"cross_eyed": True}),
+    ("ipd", {"ipd_offset": 3.0}),
+    ("ipd_neg_pad_tblr", {"ipd_offset": -2.0, "pad": 0.1, "pad_mode": "tblr"}),
+    ("pad_top", {"pad": 0.07, "pad_mode": "top"}),
+    ("pad_169", {"pad_mode": "16:9"}),
+    ("ana_wimmer2_half", {"anaglyph": "wimmer2", "half_sbs": True}),
+    ("maxw", {"max_output_width": 200, "keep_aspect_ratio": True}),
+    ("maxh_nokeep", {"max_output_height": 70}),
+]
+
+
+def gen_postprocess():
+    """postprocess_image / postprocess_padding (iw3/utils.py:394-487) executed from the reference source (iw3/utils.py
+    imports PyAV at module scope, which this image lacks, so the two functions are compiled out of the file by AST)."""
+    import ast
+    import types
+    import torchvision.transforms.functional as TF
+    from torchvision.transforms import InterpolationMode
+    from iw3.anaglyph import apply_anaglyph_redcyan
+    src = open("/root/reference/iw3/utils.py").read()
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("postprocess_padding", "postprocess_image")]
+    ns = {"torch": torch, "TF": TF, "InterpolationMode": InterpolationMode, "apply_anaglyph_redcyan": apply_anaglyph_redcyan,
+          "equirectangular_projection": None}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "/root/reference/iw3/utils.py", "exec"), ns)
+    base = dict(ipd_offset=0, rgbd=False, half_rgbd=False, pad=None, pad_mode=None, vr180=False, half_sbs=False, half_tb=False, tb=False,
+                cross_eyed=False, anaglyph=None, max_output_height=None, max_output_width=None, keep_aspect_ratio=False)
+    g = torch.Generator().manual_seed(31)
+    l = torch.rand(3, 90, 150, generator=g) * 1.1 - 0.05
+    r = torch.rand(3, 90, 150, generator=g) * 1.1 - 0.05
+    out = {"l": l, "r": r}
+    for name, kw in POSTPROCESS_CASES:
+        out["pp_" + name] = ns["postprocess_image"](l.clone(), r.clone(), types.SimpleNamespace(**{**base, **kw}))
+    save("postprocess", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -281,3 +321,5 @@ if __name__ == "__main__":
         gen_frames()
     if "row_flow" in which:
         gen_row_flow()
+    if "postprocess" in which:
+        gen_postprocess()

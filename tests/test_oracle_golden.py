@@ -299,3 +299,36 @@ def test_row_flow_oracle_matches_reference():
         assert torch.equal(l, t(g["sv_right_l"])) and float((r - t(g["sv_right_r"])).abs().max()) < 1e-5
         l, r = orf.apply_divergence_nn_LR(sd, t(g["c2"]), t(g["d2"]), 4.0, 0.6)
         assert float((l - t(g["left2"])).abs().max()) < 1e-5 and float((r - t(g["right2"])).abs().max()) < 1e-5
+
+
+def _pp_kwargs(kw):
+    kw = dict(kw)
+    if "anaglyph" in kw:
+        kw["anaglyph_type"] = kw.pop("anaglyph")
+    return kw
+
+
+def test_anaglyph_family_and_postprocess_oracle_match_reference():
+    from oracle import postprocess as opp
+    g = load_golden("anaglyph")
+    for kind in ("color", "gray", "half-color", "wimmer", "wimmer2"):
+        got = opp.anaglyph(g["l"], g["r"], kind)
+        assert np.abs(got - g[kind.replace("-", "_")]).max() < 1e-6, kind
+    pg = load_golden("postprocess")
+    cases = _postprocess_cases()
+    dub = lambda l, r, cb: oiw.dubois(torch.from_numpy(l), torch.from_numpy(r), cb).numpy()   # noqa: E731
+    for name, kw in cases:
+        got = opp.postprocess_image(pg["l"], pg["r"], dubois=dub, **_pp_kwargs(kw))
+        want = pg["pp_" + name]
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        assert np.abs(got - want).max() < 1e-5, (name, np.abs(got - want).max())   # fractional-scale AA weights: fp32 order
+
+
+def _postprocess_cases():
+    """POSTPROCESS_CASES of oracle/gen_golden.py without importing it (it imports the reference tree)."""
+    import ast
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "gen_golden.py")).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "POSTPROCESS_CASES":
+            return ast.literal_eval(node.value)
+    raise AssertionError("POSTPROCESS_CASES not found")
