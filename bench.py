@@ -399,9 +399,10 @@ def run_b200(args):
             except Exception as e:  # noqa: BLE001
                 torch.cuda.synchronize()
                 return {"error": f"{type(e).__name__}: {e}"}
-        iw3 = guarded(bench_iw3, dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if rank == 0 else None
-        upc = guarded(bench_upcunet, dev, lib, x) if rank == 0 else None
-        cfg4 = guarded(bench_8k_downscaled, dev, model) if rank == 0 else None
+        secondaries = rank == 0 and not os.environ.get("NB200_BENCH_MINIMAL")   # (set for the ncu launch-list pass)
+        iw3 = guarded(bench_iw3, dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if secondaries else None
+        upc = guarded(bench_upcunet, dev, lib, x) if secondaries else None
+        cfg4 = guarded(bench_8k_downscaled, dev, model) if secondaries else None
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
