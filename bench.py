@@ -331,6 +331,8 @@ def run_b200(args):
             os.close(saved)
     lib = _lib.lib()
     _lib.check(lib.nb200_check_device(local))
+    if os.environ.get("NB200_GRAPHS"):
+        _lib.check(lib.nb200_tune_set(9, int(os.environ["NB200_GRAPHS"])))   # CUDA-graph replay of the tile-batch forward (A/B)
 
     h, w = FRAME[args.frame]
     ntiles = frame_tiles(h, w)

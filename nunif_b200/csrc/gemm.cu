@@ -86,7 +86,8 @@ unsigned long long* g_timeline = nullptr;
 int g_tune[16] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, /*3 force gather backward warp*/ 0,
                  /*4 forced BLOCK_N*/ 0, /*5 disable GELU->128 rule*/ 0,
                  /*6 attention smem carveout %*/ 0, /*7 SIMT stem / tail convs*/ 0,
-                  /*8 programmatic dependent launch of the GEMMs*/ 1, 0, 0, 0, 0, 0, 0, 0};
+                  /*8 programmatic dependent launch of the GEMMs*/ 1,
+                  /*9 CUDA-graph replay of nb200_model_forward*/ 0, 0, 0, 0, 0, 0, 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {

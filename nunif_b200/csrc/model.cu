@@ -15,8 +15,12 @@
 #include <cstring>
 #include <cmath>
 #include <memory>
+#include <tuple>
 
 namespace nb200 {
+
+extern int g_tune[16];                 // gemm.cu (nb200_tune_set)
+extern unsigned long long* g_timeline;  // gemm.cu (nb200_debug_timeline)
 
 // ---------------------------------------------------------------------------------------------
 // weight packing
@@ -212,10 +216,45 @@ struct nb200_model {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
+    // CUDA-graph cache of nb200_model_forward, keyed by (input ptr, output ptr, n, tile, downscale); nullptr = capture failed
+    struct GraphKey {
+        const void* x; void* z; int n, T, down;
+        bool operator<(const GraphKey& o) const {
+            return std::tie(x, z, n, T, down) < std::tie(o.x, o.z, o.n, o.T, o.down);
+        }
+    };
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, int> graph_seen;
+    void clear_graphs() {
+        for (auto& kv : graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+        graph_seen.clear();
+    }
+    // frame-level buffers of nb200_tiled_render (persistent so that the captured graphs see stable pointers)
+    __half* frame_xb = nullptr; size_t frame_xb_bytes = 0;
+    __half* frame_z = nullptr; size_t frame_z_bytes = 0;
+    int ensure_frame(size_t xb_bytes, size_t z_bytes) {
+        if (xb_bytes > frame_xb_bytes) {
+            clear_graphs();
+            if (frame_xb) cudaFree(frame_xb);
+            frame_xb = nullptr; frame_xb_bytes = 0;
+            NB_CUDA(cudaMalloc((void**)&frame_xb, xb_bytes));
+            frame_xb_bytes = xb_bytes;
+        }
+        if (z_bytes > frame_z_bytes) {
+            clear_graphs();
+            if (frame_z) cudaFree(frame_z);
+            frame_z = nullptr; frame_z_bytes = 0;
+            NB_CUDA(cudaMalloc((void**)&frame_z, z_bytes));
+            frame_z_bytes = z_bytes;
+        }
+        return 0;
+    }
     template <typename T>
     T* at(size_t off) const { return reinterpret_cast<T*>(blob + off); }
     int ensure_ws(size_t bytes) {
         if (bytes <= ws_bytes) return 0;
+        clear_graphs();   // captured graphs hold pointers into the old workspace
         if (ws) cudaFree(ws);
         ws = nullptr;
         ws_bytes = 0;
@@ -490,6 +529,9 @@ extern "C" void nb200_model_destroy(nb200_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->ws) cudaFree(m->ws);
+    m->clear_graphs();
+    if (m->frame_xb) cudaFree(m->frame_xb);
+    if (m->frame_z) cudaFree(m->frame_z);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
 }
@@ -528,8 +570,41 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
     if (model_out_geometry(m, tile_size, downscale, &scale, &offset, &blend, &S)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     NB_CHECK(m->kind <= NB200_MODEL_SWIN_UNET_4X, "not an image-to-image model");
-    if (m->kind >= NB200_MODEL_SWIN_UNET_1X) return swin_forward(m, st, (const __half*)x, n, tile_size, downscale, (__half*)z);
-    return cunet_forward(m, st, (const __half*)x, n, tile_size, (__half*)z);
+    auto eager = [&]() {
+        if (m->kind >= NB200_MODEL_SWIN_UNET_1X) return swin_forward(m, st, (const __half*)x, n, tile_size, downscale, (__half*)z);
+        return cunet_forward(m, st, (const __half*)x, n, tile_size, (__half*)z);
+    };
+    // CUDA graphs (g_tune[9]): the ~80 launches of one tile batch are replayed as one graph launch once the same
+    // (buffers, shape) has been seen twice; removes most of the inter-kernel launch latency (≈7 % of a 4K frame,
+    // profiles/r1/launches_bench_step_summary.txt).  Never while the event profiler or the timeline probe is on.
+    if (!g_tune[9] || g_prof_enabled.load(std::memory_order_relaxed) || g_timeline) return eager();
+    const nb200_model::GraphKey key{x, z, n, tile_size, downscale};
+    auto it = m->graphs.find(key);
+    if (it != m->graphs.end()) {
+        if (!it->second) return eager();
+        NB_CUDA(cudaGraphLaunch(it->second, st));
+        return 0;
+    }
+    if (++m->graph_seen[key] < 2) return eager();           // first sighting: eager (also sizes the workspace, sets func attributes)
+    if (m->graphs.size() > 256) m->clear_graphs();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int rc = 1;
+    if (e == cudaSuccess) {
+        rc = eager();
+        e = cudaStreamEndCapture(st, &graph);
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != 0 || !exec) {
+        cudaGetLastError();                                  // capture is not available for this sequence: stay eager
+        m->graphs[key] = nullptr;
+        return eager();
+    }
+    m->graphs[key] = exec;
+    NB_CUDA(cudaGraphLaunch(exec, st));
+    return 0;
 }
 
 extern "C" int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, int W, int tile_size, int batch_size,
@@ -544,10 +619,11 @@ extern "C" int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, 
     if (nb200_tile_config_create(H, W, scale, offset, tile_size, blend, &cfg)) return 1;
     const int ntiles = cfg.h_blocks * cfg.w_blocks;
     // frame-level buffers (stream-ordered): the unfolded tile batch and every tile's output
-    __half *xb = nullptr, *zall = nullptr;
+    // frame-level buffers: the unfolded tile batch and every tile's output (persistent per model; not re-entrant:
+    // one render at a time per model handle, like the reference's module)
     const size_t xb_elems = (size_t)batch_size * tile_size * tile_size * 8, z_tile = (size_t)3 * S * S;
-    NB_CUDA(cudaMallocAsync((void**)&xb, xb_elems * 2, st));
-    NB_CUDA(cudaMallocAsync((void**)&zall, (size_t)ntiles * z_tile * 2, st));
+    if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * 2)) return 1;
+    __half *xb = m->frame_xb, *zall = m->frame_z;
     int rc = 0;
     for (int t0 = 0; t0 < ntiles && !rc; t0 += batch_size) {
         const int nb = ntiles - t0 < batch_size ? ntiles - t0 : batch_size;
@@ -555,8 +631,6 @@ extern "C" int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, 
         if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile, stream);
     }
     if (!rc) rc = nb200_tile_gather_blend(zall, C, &cfg, scale, offset, tile_size, blend, out, stream);
-    cudaFreeAsync(xb, st);
-    cudaFreeAsync(zall, st);
     return rc;
 }
 
@@ -583,8 +657,8 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     const size_t oplane = (size_t)cfg.y_h * cfg.y_w;
     NB_CUDA(cudaMallocAsync((void**)&xd, (size_t)C * H * W * 4, st));
     NB_CUDA(cudaMallocAsync((void**)&od, (size_t)C * oplane * 4, st));
-    NB_CUDA(cudaMallocAsync((void**)&xb, xb_elems * 2, st));
-    NB_CUDA(cudaMallocAsync((void**)&zall, (size_t)ntiles * z_tile * 2, st));
+    if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * 2)) return 1;
+    xb = m->frame_xb; zall = m->frame_z;
     NB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)C * H * W * 4, cudaMemcpyHostToDevice, st));
     int rc = 0, rows_done = 0;
     for (int t0 = 0; t0 < ntiles && !rc; t0 += batch_size) {
@@ -619,8 +693,7 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     NB_CUDA(cudaEventDestroy(ev_end));
     cudaFreeAsync(xd, st);
     cudaFreeAsync(od, st);
-    cudaFreeAsync(xb, st);
-    cudaFreeAsync(zall, st);
+
     return rc;
 }
 

@@ -72,6 +72,28 @@ def test_cunet_tail_tensor_core_and_simt_kernels_agree(name, up):
     assert stats(a, b)["max"] < 2e-3, stats(a, b)
 
 
+def test_cuda_graph_replay_is_bit_identical():
+    """nb200_tune_set(9, 1): the tile-batch forward is captured into a CUDA graph on its second sighting and replayed; the
+    rendered frame must not change, across several frames and for a batch size that leaves a ragged last batch."""
+    from nunif_b200 import _lib
+    from nunif_b200.nunif.models import create_model
+    from nunif_b200.nunif.render import tiled_render
+    m = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), DEV)
+    imgs = [synth.synth_image(60 + i, 3, 150, 200).to(DEV) for i in range(3)]
+    with torch.no_grad():
+        want = [tiled_render(im, m, tile_size=64, batch_size=5) for im in imgs]
+        _lib.lib().nb200_tune_set(9, 1)
+        try:
+            for rep in range(3):
+                for im, w in zip(imgs, want):
+                    assert torch.equal(tiled_render(im, m, tile_size=64, batch_size=5), w), rep
+            host = tiled_render(imgs[0].cpu().pin_memory(), m, tile_size=64, batch_size=5)
+            torch.cuda.synchronize()
+            assert torch.equal(host, want[0].cpu())
+        finally:
+            _lib.lib().nb200_tune_set(9, 0)
+
+
 def test_swin_stem_tensor_core_and_simt_kernels_agree():
     from nunif_b200 import _lib
     from nunif_b200.nunif.models import create_model
