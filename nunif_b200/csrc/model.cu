@@ -225,10 +225,12 @@ struct nb200_model {
     };
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, int> graph_seen;
+    std::map<GraphKey, uint64_t> graph_launches;   // kernel launches one replay stands for (nb200_launch_count)
     void clear_graphs() {
         for (auto& kv : graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
         graphs.clear();
         graph_seen.clear();
+        graph_launches.clear();
     }
     // frame-level buffers of nb200_tiled_render (persistent so that the captured graphs see stable pointers)
     __half* frame_xb = nullptr; size_t frame_xb_bytes = 0;
@@ -583,6 +585,7 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
     if (it != m->graphs.end()) {
         if (!it->second) return eager();
         NB_CUDA(cudaGraphLaunch(it->second, st));
+        g_launches.fetch_add(m->graph_launches[key]);
         return 0;
     }
     if (++m->graph_seen[key] < 2) return eager();           // first sighting: eager (also sizes the workspace, sets func attributes)
@@ -590,10 +593,12 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
     int rc = 1;
+    const uint64_t l0 = g_launches.load();
     if (e == cudaSuccess) {
         rc = eager();
         e = cudaStreamEndCapture(st, &graph);
     }
+    const uint64_t captured = g_launches.load() - l0;
     cudaGraphExec_t exec = nullptr;
     if (e == cudaSuccess && rc == 0 && graph) e = cudaGraphInstantiate(&exec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
@@ -603,7 +608,8 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
         return eager();
     }
     m->graphs[key] = exec;
-    NB_CUDA(cudaGraphLaunch(exec, st));
+    m->graph_launches[key] = captured;
+    NB_CUDA(cudaGraphLaunch(exec, st));                      // (the launches counted during capture stand for this first replay)
     return 0;
 }
 
