@@ -1,0 +1,88 @@
+"""CPU-only checks of host-side logic of the Python mirror (no CUDA calls): checkpoint-directory rules of Waifu2x
+(waifu2x/utils.py:128-216), method normalisation (waifu2x/hub.py:151-163), edge_dilation parsing (iw3/dilation.py:5-27),
+the learned-warp feature values (iw3/backward_warp.py:8-15) and the launch-list summariser."""
+import os
+import types
+import pytest
+
+
+class _Fake:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def to_2x(self):
+        return _Fake(self.tag + "->2x")
+
+    def to_1x(self):
+        return _Fake(self.tag + "->1x")
+
+
+def _ctx(tmp_path, files):
+    from nunif_b200.waifu2x.utils import Waifu2x
+    for f in files:
+        open(os.path.join(tmp_path, f), "w").close()
+    w = Waifu2x(str(tmp_path), [0])
+    w.load_model_by_name = lambda filename: _Fake(filename)      # no GPU: record which file would be loaded
+    return w
+
+
+def test_waifu2x_checkpoint_rules_4x_only_directory(tmp_path):
+    w = _ctx(tmp_path, ["scale4x.pth", "noise0_scale4x.pth", "noise1_scale4x.pth", "noise2_scale4x.pth", "noise3_scale4x.pth"])
+    w.load_model_all(load_4x=True)
+    assert w.scale4x_model.tag == "scale4x.pth" and w.scale_model.tag == "scale4x.pth->2x"
+    for n in range(4):
+        assert w.noise_scale4x_models[n].tag == f"noise{n}_scale4x.pth"
+        assert w.noise_scale_models[n].tag == f"noise{n}_scale4x.pth->2x"
+        assert w.noise_models[n].tag == f"noise{n}_scale4x.pth->1x"
+
+
+def test_waifu2x_checkpoint_rules_prefer_native_files_and_errors(tmp_path):
+    w = _ctx(tmp_path, ["scale2x.pth", "noise2.pth", "noise2_scale2x.pth"])
+    w.load_model("noise_scale", 2)
+    assert w.noise_scale_models[2].tag == "noise2_scale2x.pth" and w.scale_model.tag == "scale2x.pth"   # companion scale model
+    w.load_model("noise", 2)
+    assert w.noise_models[2].tag == "noise2.pth"
+    with pytest.raises(FileNotFoundError):
+        w.load_model("scale4x", -1)
+    with pytest.raises(FileNotFoundError):
+        w.load_model("noise", 1)                 # neither noise1.pth nor noise1_scale4x.pth
+    with pytest.raises(AssertionError):
+        w.load_model("noise", 7)
+    with pytest.raises(ValueError):
+        w._load_model("bogus", 0)
+    first = w.noise_models[2]
+    w.load_model("noise", 2)
+    assert w.noise_models[2] is first            # cached
+
+
+def test_normalize_method_and_dilation_parse():
+    from nunif_b200.waifu2x.hub import Waifu2xImageModel
+    nm = Waifu2xImageModel.normalize_method
+    assert nm("scale2x", -1) == "scale" and nm("scale", 1) == "noise_scale" and nm("scale4x", 0) == "noise_scale4x"
+    assert nm("noise_scale2x", 2) == "noise_scale" and nm(None, 0) is None and nm("noise", 3) == "noise"
+    from nunif_b200.iw3.dilation import edge_dilation_parse, edge_dilation_is_enabled
+    assert edge_dilation_parse(2) == (2, 2) or tuple(edge_dilation_parse(2)) == (2, 2)
+    assert tuple(edge_dilation_parse([2, 1])) == (2, 1)
+    assert edge_dilation_is_enabled([0, 1]) and not edge_dilation_is_enabled(0) and not edge_dilation_is_enabled([0, 0])
+    with pytest.raises((ValueError, TypeError)):
+        edge_dilation_parse("x")
+
+
+def test_row_flow_feature_values():
+    from nunif_b200.iw3.row_flow import make_divergence_feature_value
+    d, c = make_divergence_feature_value(2.0, 0.5, 1920)
+    assert d == pytest.approx(2.0 * 0.5 * 0.01 * 1920 / 32.0) and c == pytest.approx(-2.0 * 0.5 * 0.01 * 1920 * 0.5 / 32.0)
+
+
+def test_bench_launch_list_summary_agrees_with_live_shares():
+    """The committed ncu launch list of the bench command and the live kernel-class shares must agree (task contract)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "summarize_bench_launches.py"),
+                          os.path.join(root, "profiles", "r1", "launches_bench_step.csv"),
+                          os.path.join(root, "profiles", "r1", "bench_r1_final_e.json")], capture_output=True, text=True, check=True).stdout
+    ncu = eval(out.split("class shares (ncu):")[1].splitlines()[0].strip())
+    live = eval(out.split("class shares (bench):")[1].splitlines()[0].strip())
+    for k in ("gemm", "window_attention"):
+        assert abs(ncu[k] - live[k]) < 0.03, (k, ncu[k], live[k])
