@@ -81,7 +81,7 @@ def test_find_valid_tile_size_host():
     assert m_s.find_valid_tile_size(None) == 256
 
 
-def test_da_preprocess_size_host_rule_bit_exact():
+def test_da_preprocess_size_host_rule_bit_exact(lib):
     """nb200_da_preprocess_size is host integer logic (depth_anything_model.py:69-101): check it against the sizes the
     reference produced (tests/golden/frames.npz) without a GPU."""
     from tests.util import load_golden
@@ -92,7 +92,7 @@ def test_da_preprocess_size_host_rule_bit_exact():
     assert preprocess_size(1080, 1920) == (392, 686)
 
 
-def test_zoe_preprocess_size_host_rule_bit_exact():
+def test_zoe_preprocess_size_host_rule_bit_exact(lib):
     """nb200_zoe_preprocess_size (zoedepth_model.py:30-71, incl. Python's round-half-even) against the reference's sizes."""
     from tests.util import load_golden
     from nunif_b200.iw3.zoedepth_preprocess import preprocess_size
