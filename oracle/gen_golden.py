@@ -306,9 +306,29 @@ def gen_postprocess():
     save("postprocess", **out)
 
 
+def gen_depth_scaler():
+    """EMAMinMaxScaler (iw3/depth_scaler.py:64-142) over a sequence of frames, look-ahead buffering and flush included."""
+    from iw3.depth_scaler import EMAMinMaxScaler
+    g = torch.Generator().manual_seed(41)
+    frames = [torch.rand(1, 12, 17, generator=g) * (1.0 + 0.5 * i) + 0.1 * ((-1) ** i) * i for i in range(9)]
+    frames[4] = torch.zeros(1, 12, 17)        # an all-equal frame (scale == 0 branch of a stateless scaler)
+    out = {"frames": torch.stack(frames)}
+    for tag, kw in (("simple", dict(decay=0, buffer_size=1)), ("ema", dict(decay=0.75, buffer_size=1)),
+                    ("window", dict(decay=0.9, buffer_size=4)), ("max", dict(decay=0.5, buffer_size=2, mode="max"))):
+        sc = EMAMinMaxScaler(**kw)
+        res = []
+        for f in frames:
+            r = sc.update(f)
+            res.append(torch.full_like(f, float("nan")) if r is None else r)
+        tail = sc.flush()
+        out[tag + "_update"] = torch.stack(res)
+        out[tag + "_flush"] = torch.stack(tail) if tail else torch.zeros(0, 1, 12, 17)
+    save("depth_scaler", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess", "depth_scaler"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -323,3 +343,5 @@ if __name__ == "__main__":
         gen_row_flow()
     if "postprocess" in which:
         gen_postprocess()
+    if "depth_scaler" in which:
+        gen_depth_scaler()

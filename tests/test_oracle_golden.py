@@ -332,3 +332,24 @@ def _postprocess_cases():
         if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "POSTPROCESS_CASES":
             return ast.literal_eval(node.value)
     raise AssertionError("POSTPROCESS_CASES not found")
+
+
+def test_ema_minmax_scaler_oracle_matches_reference():
+    """Stateful normaliser of --ema-normalize: pinned now, ported in a later round."""
+    from oracle.depth_scaler import EMAMinMaxScaler
+    g = load_golden("depth_scaler")
+    frames = g["frames"]
+    for tag, kw in (("simple", dict(decay=0, buffer_size=1)), ("ema", dict(decay=0.75, buffer_size=1)),
+                    ("window", dict(decay=0.9, buffer_size=4)), ("max", dict(decay=0.5, buffer_size=2, mode="max"))):
+        sc = EMAMinMaxScaler(**kw)
+        for i, f in enumerate(frames):
+            r = sc.update(f)
+            want = g[tag + "_update"][i]
+            if r is None:
+                assert np.isnan(want).all(), (tag, i)
+            else:
+                assert np.abs(r - want).max() < 1e-6, (tag, i, np.abs(r - want).max())
+        tail = sc.flush()
+        assert len(tail) == g[tag + "_flush"].shape[0], tag
+        for r, want in zip(tail, g[tag + "_flush"]):
+            assert np.abs(r - want).max() < 1e-6, tag
