@@ -303,6 +303,8 @@ def gen_postprocess():
     out = {"l": l, "r": r}
     for name, kw in POSTPROCESS_CASES:
         out["pp_" + name] = ns["postprocess_image"](l.clone(), r.clone(), types.SimpleNamespace(**{**base, **kw}))
+    from iw3.equirectangular import equirectangular_projection
+    out["vr180_l"] = equirectangular_projection(l.clamp(0, 1))
     save("postprocess", **out)
 
 

@@ -109,3 +109,53 @@ def postprocess_image(left, right, ipd_offset=0, pad=None, pad_mode=None, half_s
         nw -= nw % 2
         sbs = np.clip(resize_bicubic_aa(sbs, nh, nw), 0, 1)
     return sbs
+
+
+def _grid_sample_bicubic_zeros(c, gx, gy):
+    """F.grid_sample(mode="bicubic", padding_mode="zeros", align_corners=True) for one (C,H,W) image and (Ho,Wo) grids in
+    [-1,1] (ATen grid_sampler_2d: A = -0.75, out-of-range taps contribute 0).  Explicit 4x4 gather."""
+    f = np.float32
+    C, H, W = c.shape
+    ix = ((gx + f(1)) / f(2)) * f(W - 1)
+    iy = ((gy + f(1)) / f(2)) * f(H - 1)
+    ix0, iy0 = np.floor(ix), np.floor(iy)
+    tx, ty = (ix - ix0).astype(np.float32), (iy - iy0).astype(np.float32)
+
+    def coeffs(t):
+        A = f(-0.75)
+        def c1(x): return ((A + f(2)) * x - (A + f(3))) * x * x + f(1)
+        def c2(x): return ((A * x - f(5) * A) * x + f(8) * A) * x - f(4) * A
+        return [c2(t + f(1)), c1(t), c1(f(1) - t), c2(f(2) - t)]
+    wx, wy = coeffs(tx), coeffs(ty)
+    out = np.zeros((C,) + gx.shape, dtype=np.float32)
+    for a in range(4):
+        yy = (iy0 + a - 1).astype(np.int64)
+        row = np.zeros_like(out)
+        for b in range(4):
+            xx = (ix0 + b - 1).astype(np.int64)
+            ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+            v = c[:, np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)] * ok
+            row = row + v * wx[b]
+        out = out + row * wy[a]
+    return out
+
+
+def equirectangular_projection(c):
+    """iw3/equirectangular.py:7-40 (VR180 output): zero-pad to a square of 1.5x the longer edge, then bicubic grid_sample
+    through the tan() mesh.  Pinned for the round that ports it (the engine raises NotImplementedError for vr180 today)."""
+    import math
+    f = np.float32
+    h, w = c.shape[1:]
+    max_edge = max(h, w)
+    output_size = max_edge + max_edge // 2
+    pad_w, pad_h = (output_size - w) // 2, (output_size - h) // 2
+    c = np.pad(np.asarray(c, dtype=np.float32), ((0, 0), (pad_h, pad_h), (pad_w, pad_w)))
+    h, w = c.shape[1:]
+    import torch   # linspace with torch's fp32 semantics (symmetric evaluation)
+    y = torch.linspace(-1, 1, h).numpy()[:, None].repeat(w, 1)
+    x = torch.linspace(-1, 1, w).numpy()[None, :].repeat(h, 0)
+    az, el = x * f(math.pi * 0.5), y * f(math.pi * 0.5)
+    k = f(max_edge / output_size)
+    mesh_x = k * np.tan(az).astype(np.float32)
+    mesh_y = k * (np.tan(el).astype(np.float32) / np.cos(az).astype(np.float32))
+    return np.clip(_grid_sample_bicubic_zeros(c, mesh_x.astype(np.float32), mesh_y.astype(np.float32)), 0, 1)
