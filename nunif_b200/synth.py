@@ -293,3 +293,44 @@ def row_flow_v3_state_dict(seed=0):
     sd["last_layer.1.bias"] = rn(1, std=0.1)
     sd["delta_scale"] = torch.tensor(1.0 / 127.0)
     return sd
+
+
+def _window_bias_buffers(ws):
+    """`index` / `delta` buffers of WindowScoreBias (nunif/modules/attention.py:347-372) for a square window."""
+    N = ws * ws
+    pos = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij"), dim=2).reshape(N, 2)
+    delta = [tuple(d) for d in (pos[:, None, :] - pos[None, :, :]).reshape(N * N, 2).tolist()]
+    uniq = sorted(set(delta))
+    index = torch.tensor([uniq.index(d) for d in delta], dtype=torch.int64)
+    ud = torch.tensor(uniq, dtype=torch.float32)
+    return index, ud / ud.abs().max()
+
+
+def depth_aa_state_dict(seed=0):
+    """Seeded weights with the key names of `iw3.depth_aa` (iw3/models/depth_aa.py); the released model zero-initialises
+    proj_out, here every tensor is random so that the filter is non-trivial."""
+    g = torch.Generator().manual_seed(30_000 + seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    C = 32
+    sd = {"proj_in.weight": rn(C, 4, 1, 1, std=0.5), "proj_in.bias": rn(C, std=0.05)}
+    for i in range(3):
+        p = f"blocks.{i}."
+        sd[p + "mha.mha.qkv_proj.weight"] = rn(3 * C, C, std=1.0 / C ** 0.5)
+        sd[p + "mha.mha.qkv_proj.bias"] = rn(3 * C, std=0.05)
+        sd[p + "mha.mha.head_proj.weight"] = rn(C, C, std=0.6 / C ** 0.5)
+        sd[p + "mha.mha.head_proj.bias"] = rn(C, std=0.02)
+        sd[p + "conv_mlp.0.weight"] = rn(C, C, 1, 1, std=1.0 / C ** 0.5)
+        sd[p + "conv_mlp.0.bias"] = rn(C, std=0.05)
+        sd[p + "conv_mlp.3.weight"] = rn(C, C, 3, 3, std=0.6 / (9 * C) ** 0.5)
+        sd[p + "conv_mlp.3.bias"] = rn(C, std=0.02)
+        sd[p + "bias.index"], sd[p + "bias.delta"] = _window_bias_buffers(8)
+        sd[p + "bias.to_bias.0.weight"] = rn(16, 2, std=1.0)
+        sd[p + "bias.to_bias.0.bias"] = rn(16, std=0.3)
+        sd[p + "bias.to_bias.2.weight"] = rn(1, 16, std=0.7)
+        sd[p + "bias.to_bias.2.bias"] = rn(1, std=0.1)
+    sd["proj_out.weight"] = rn(4, C, 1, 1, std=0.05)
+    sd["proj_out.bias"] = rn(4, std=0.01)
+    return sd

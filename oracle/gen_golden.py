@@ -328,9 +328,21 @@ def gen_depth_scaler():
     save("depth_scaler", **out)
 
 
+def gen_depth_aa():
+    """iw3.depth_aa (iw3/models/depth_aa.py): forward (eval clamp) and infer."""
+    from nunif.models import create_model
+    import iw3.models  # noqa: F401
+    m = create_model("iw3.depth_aa").eval()
+    m.load_state_dict(synth.depth_aa_state_dict(0), strict=True)
+    g = torch.Generator().manual_seed(51)
+    x = torch.rand(2, 1, 70, 90, generator=g)
+    xi = synth.synth_depth(7, 1, 98, 130) * 6.0 + 1.5
+    save("depth_aa", x=x, y=m(x), xi=xi, yi=m.infer(xi))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess", "depth_scaler"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess", "depth_scaler", "depth_aa"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -347,3 +359,5 @@ if __name__ == "__main__":
         gen_postprocess()
     if "depth_scaler" in which:
         gen_depth_scaler()
+    if "depth_aa" in which:
+        gen_depth_aa()

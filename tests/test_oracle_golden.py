@@ -364,3 +364,14 @@ def test_equirectangular_oracle_matches_reference():
     assert got.shape == want.shape
     d = np.abs(got - want)
     assert d.max() < 5e-5 and d.mean() < 1e-6, (d.max(), d.mean())
+
+
+def test_depth_aa_oracle_matches_reference():
+    """iw3.depth_aa learned post-filter: pinned now, ported in a later round."""
+    from oracle import depth_aa as oaa
+    g = load_golden("depth_aa")
+    sd = synth.depth_aa_state_dict(0)
+    with torch.no_grad():
+        assert float((oaa.depth_aa_forward(sd, t(g["x"])) - t(g["y"])).abs().max()) < 1e-5
+        yi = oaa.depth_aa_infer(sd, t(g["xi"]))
+        assert float((yi - t(g["yi"])).abs().max()) < 1e-4 * float(t(g["yi"]).abs().max())
