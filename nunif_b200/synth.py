@@ -334,3 +334,33 @@ def depth_aa_state_dict(seed=0):
     sd["proj_out.weight"] = rn(4, C, 1, 1, std=0.05)
     sd["proj_out.bias"] = rn(4, std=0.01)
     return sd
+
+
+def mlbw_state_dict(seed=0, num_layers=2):
+    """Seeded weights with the key names of `sbs.mlbw` (iw3/models/mlbw.py, MLBW(num_layers, base_dim=32))."""
+    g = torch.Generator().manual_seed(40_000 + seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    C = 32 * num_layers
+    c1 = C // 8
+    sd = {"lv1_in.1.weight": rn(c1, 3, 1, 9, std=1.0 / 27 ** 0.5), "lv1_in.1.bias": rn(c1, std=0.05)}
+    for i in range(4):
+        p = f"lv2.{i}."
+        sd[p + "mha.mha.qkv_proj.weight"] = rn(3 * C, C, std=1.0 / C ** 0.5)
+        sd[p + "mha.mha.qkv_proj.bias"] = rn(3 * C, std=0.05)
+        sd[p + "mha.mha.head_proj.weight"] = rn(C, C, std=0.6 / C ** 0.5)
+        sd[p + "mha.mha.head_proj.bias"] = rn(C, std=0.02)
+        sd[p + "conv_mlp.0.weight"] = rn(C, C, 1, 1, std=1.0 / C ** 0.5)
+        sd[p + "conv_mlp.0.bias"] = rn(C, std=0.05)
+        sd[p + "conv_mlp.3.weight"] = rn(C, C, 3, 3, std=0.6 / (9 * C) ** 0.5)
+        sd[p + "conv_mlp.3.bias"] = rn(C, std=0.02)
+        sd[p + "bias.index"], sd[p + "bias.delta"] = _window_bias_buffers(4)
+        sd[p + "bias.to_bias.0.weight"] = rn(8, 2, std=1.0)
+        sd[p + "bias.to_bias.0.bias"] = rn(8, std=0.3)
+        sd[p + "bias.to_bias.2.weight"] = rn(1, 8, std=0.7)
+        sd[p + "bias.to_bias.2.bias"] = rn(1, std=0.1)
+    sd["lv1_out.1.weight"] = rn(2 * num_layers, c1, 1, 9, std=1.5 / (9 * c1) ** 0.5)
+    sd["lv1_out.1.bias"] = rn(2 * num_layers, std=0.1)
+    return sd

@@ -340,9 +340,25 @@ def gen_depth_aa():
     save("depth_aa", x=x, y=m(x), xi=xi, yi=m.infer(xi))
 
 
+def gen_mlbw():
+    """sbs.mlbw (iw3/models/mlbw.py) in delta_output mode + apply_divergence_nn_LR -> apply_divergence_nn_delta_weight."""
+    from nunif.models import create_model
+    import iw3.models  # noqa: F401
+    from iw3.backward_warp import apply_divergence_nn_LR, make_input_tensor
+    m = create_model("sbs.mlbw").eval()
+    m.load_state_dict(synth.mlbw_state_dict(0), strict=True)
+    m.delta_output = True
+    d = synth.synth_depth(3, 2, 70, 130)
+    x = torch.stack([make_input_tensor(None, d[i], divergence=2.0, convergence=0.5, image_width=130) for i in range(2)])
+    delta, lw = m(x)
+    c = torch.stack([synth.synth_image(4 + i, 3, 140, 260) for i in range(2)])
+    l, r = apply_divergence_nn_LR(m, c, d, 2.0, 0.5, steps=1, enable_amp=False)
+    save("mlbw", d=d, x=x, delta=delta, layer_weight=lw, left=l, right=r)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess", "depth_scaler", "depth_aa"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess", "depth_scaler", "depth_aa", "mlbw"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -361,3 +377,5 @@ if __name__ == "__main__":
         gen_depth_scaler()
     if "depth_aa" in which:
         gen_depth_aa()
+    if "mlbw" in which:
+        gen_mlbw()

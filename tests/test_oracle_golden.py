@@ -375,3 +375,17 @@ def test_depth_aa_oracle_matches_reference():
         assert float((oaa.depth_aa_forward(sd, t(g["x"])) - t(g["y"])).abs().max()) < 1e-5
         yi = oaa.depth_aa_infer(sd, t(g["xi"]))
         assert float((yi - t(g["yi"])).abs().max()) < 1e-4 * float(t(g["yi"]).abs().max())
+
+
+def test_mlbw_oracle_matches_reference():
+    """sbs.mlbw multi-layer learned warp: pinned now, ported in a later round."""
+    from oracle import mlbw as om
+    g = load_golden("mlbw")
+    sd = synth.mlbw_state_dict(0)
+    c = torch.stack([synth.synth_image(4 + i, 3, 140, 260) for i in range(2)])
+    with torch.no_grad():
+        delta, lw = om.mlbw_delta(sd, t(g["x"]))
+        assert float((delta - t(g["delta"])).abs().max()) < 1e-5 and float((lw - t(g["layer_weight"])).abs().max()) < 1e-6
+        l = om.apply_divergence_mlbw(sd, c, t(g["d"]), 2.0, 0.5, -1)
+        r = om.apply_divergence_mlbw(sd, c, t(g["d"]), 2.0, 0.5, 1)
+        assert float((l - t(g["left"])).abs().max()) < 1e-5 and float((r - t(g["right"])).abs().max()) < 1e-5
