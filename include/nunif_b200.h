@@ -226,6 +226,22 @@ int nb200_conv_gemm_f16(const void* A, int B, int Hi, int Wi, int Ci, int Cin, i
 int nb200_window_attention_f16(const void* qkv, const float* bias_table, void* out, int B,
                                int H, int W, int C, int heads, int shift, void* stream);
 
+/* Fused tail of one SwinTransformerBlock (torchvision swin_transformer.py:228 proj, :453-455; MLP = Linear-GELU-Linear,
+ * ratio 2, Identity norms: waifu2x/models/swin_unet.py:16-17,31), one tcgen05 kernel (csrc/swin_fused_mlp.cu):
+ *   x1 = x + att @ wp^T + bp   (att == NULL: x1 = x);   x <- x1 + gelu(x1 @ w1^T + b1) @ w2^T + b2
+ * x, att: [T][C] fp16 (x updated in place); wp [C][C], w1 [2C][C], w2 [C][2C] fp16; biases fp32.  C in {96, 192}. */
+int nb200_swin_mlp_fused_f16(void* x, const void* att, long long T, int C, const void* wp,
+                             const float* bp, const void* w1, const float* b1, const void* w2,
+                             const float* b2, void* stream);
+
+/* Fused head of one SwinTransformerBlock: qkv Linear + shifted 6x6 window attention (swin_transformer.py:166-221;
+ * everything but the proj Linear), one kernel (csrc/swin_fused_attn.cu): the qkv GEMM runs on tcgen05, q/k/v stay in
+ * shared memory.  x, att: [B][H][W][C] fp16; wqkv [3C][C] fp16 and bqkv [3C] fp32 in the reference's row order
+ * (q | k | v); bias_table fp32 [121][6] (relative_position_bias_table).  C in {96, 192}, 6 heads. */
+int nb200_swin_attn_fused_f16(const void* x, const void* wqkv, const float* bqkv,
+                              const float* bias_table, void* att, int B, int H, int W, int C,
+                              int shift, void* stream);
+
 /* Frame-edge conversions (nunif/utils/video.py:218-223 to_tensor, :236-246 from_tensor,
  * iw3/utils.py:274-289 hwc_to_chw_float): x [B][H][W][3] uint8 (bits=8) or uint16 (bits=16)
  * <-> [B][3][H][W] fp32 in [0,1]; the fp32 -> integer direction rounds half to even. */

@@ -86,6 +86,10 @@ SIGNATURES = {
     "nb200_profile_enable": (c_int, [c_int]),
     "nb200_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "nb200_profile_dump": (c_int, [c_char_p, c_size_t]),
+    "nb200_swin_mlp_fused_f16": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    "nb200_swin_attn_fused_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p]),
     "nb200_window_attention_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

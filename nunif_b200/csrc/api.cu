@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <vector>
+#include <map>
 
 namespace nb200 {
 thread_local std::string g_last_error;
@@ -21,7 +22,7 @@ static std::vector<ProfRec> g_prof_recs;
 static std::vector<cudaEvent_t> g_prof_pool;
 static const char* kCatNames[PC_COUNT] = {"gemm", "window_attention", "stem_conv", "to_image", "tile_unfold", "tile_blend",
                                           "se_block", "tail_conv", "forward_warp", "backward_warp", "dilate_edge",
-                                          "minmax_map", "other"};
+                                          "minmax_map", "other", "fused_mlp", "fused_attn"};
 
 static cudaEvent_t prof_event() {
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
@@ -38,6 +39,33 @@ void prof_begin(cudaStream_t st, int cat, double work, double rb, double wb) {
 void prof_end(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().b, st);
+}
+
+static std::mutex g_attr_mu;
+static std::map<std::pair<int, const void*>, size_t> g_dyn_smem;
+int ensure_dyn_smem(const void* func, size_t bytes) {
+    int dev = 0;
+    NB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    size_t& have = g_dyn_smem[{dev, func}];
+    if (bytes > have && bytes > 48 * 1024) {
+        NB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return 0;
+}
+int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
 }
 }  // namespace nb200
 

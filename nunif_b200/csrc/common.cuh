@@ -42,7 +42,7 @@ inline int fail(const std::string& msg) {
 
 // ---- optional in-library kernel timing (bench.py roofline): CUDA events around each launch
 enum ProfCat : int { PC_GEMM = 0, PC_ATTN, PC_STEM, PC_TOIMG, PC_UNFOLD, PC_BLEND, PC_SE, PC_TAIL, PC_WARP_FW, PC_WARP_BW,
-                     PC_DILATE, PC_MINMAX, PC_OTHER, PC_COUNT };
+                     PC_DILATE, PC_MINMAX, PC_OTHER, PC_FUSED_MLP, PC_FUSED_ATTN, PC_COUNT };
 extern std::atomic<int> g_prof_enabled;
 void prof_begin(cudaStream_t st, int cat, double work, double rbytes, double wbytes);
 void prof_end(cudaStream_t st);
@@ -67,6 +67,12 @@ int tile_gather_blend_rows(const void* z_all, int C, const ::nb200_tile_config* 
 // GEMM, gemm.cu launch_p) be scheduled as soon as every CTA of this grid has issued it or exited; the successor blocks in
 // griddepcontrol.wait until this grid has completed and flushed.  A no-op for ordinary successors.
 #define NB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: cache the configured size per (device, function)
+// (api.cu).  Thread-safe; a second device in the same process gets its own opt-in.
+int ensure_dyn_smem(const void* func, size_t bytes);
+// multiprocessor count of the CURRENT device (cached per device)
+int device_sm_count();
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -317,11 +317,7 @@ static int launch_tail_mma(cudaStream_t st, const __half* x, const float* wt, co
                            int Hi, int Wi, int Ho, int Wo, int z1H, int z1W, int clip) {
     constexpr int TAPS = MODE == 0 ? 9 : 16, WR = MODE == 0 ? 4 : 2;
     const size_t smem = (size_t)(TAPS * 512 + WR * TC_WC * TC_PS) * sizeof(__half);
-    static bool cfg = false;
-    if (!cfg) {
-        NB_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
-    }
+    if (ensure_dyn_smem((const void*)tail_conv_mma_kernel<MODE, EPI>, smem)) return 1;
     const int npx = MODE == 1 ? Wo / 2 : Wo;
     const dim3 grid(cdiv(npx, 64), MODE == 0 ? cdiv(Ho, 2) : Ho, n);
     tail_conv_mma_kernel<MODE, EPI><<<grid, 256, smem, st>>>(x, wt, bias, out, z1, Hi, Wi, Ho, Wo, z1H, z1W, clip);

@@ -406,11 +406,7 @@ int da_add_layernorm(cudaStream_t st, float* X32, const __half* delta, const flo
 
 int da_attention(cudaStream_t st, const __half* qkv, __half* out, int B, int N, int heads) {
     const size_t smem = (size_t)(FA_BM + 4 * FA_BN) * FA_LD * sizeof(__half);
-    static bool cfg = false;
-    if (!cfg) {
-        NB_CUDA(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
-    }
+    if (ensure_dyn_smem((const void*)flash_attention_kernel, smem)) return 1;
     const double T = (double)B * N * heads * FA_D;
     ProfScope ps(st, PC_ATTN, 4.0 * T * N, T * 3 * 2, T * 2);
     flash_attention_kernel<<<dim3(cdiv(N, FA_BM), heads, B), 128, smem, st>>>(qkv, out, N, heads);

@@ -2,6 +2,7 @@
 #include "gemm.h"
 #include "gemm_tcgen05.cuh"
 #include "gemm_persistent.cuh"
+#include "tmap.h"
 #include <mutex>
 #include <cstdlib>
 
@@ -26,7 +27,7 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                   const cuuint32_t* box, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return fail("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -43,11 +44,7 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
 template <int BN, int BK>
 static int launch_t(cudaStream_t st, const GemmMaps& maps, const GemmParams& p, int m_tiles, int n_tiles) {
     using Cfg = GemmCfg<BN, BK>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    if (ensure_dyn_smem((const void*)gemm_conv_kernel<BN, BK>, Cfg::SMEM_BYTES)) return 1;
     gemm_conv_kernel<BN, BK><<<dim3((unsigned)m_tiles * n_tiles), GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
     NB_LAUNCHED();
     return 0;
@@ -68,16 +65,7 @@ static int launch_bn(int bn, cudaStream_t st, const GemmMaps& maps, const GemmPa
     return fail("unsupported BLOCK_N");
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*barriers*/;
 
@@ -87,15 +75,12 @@ int g_tune[16] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG
                  /*4 forced BLOCK_N*/ 0, /*5 disable GELU->128 rule*/ 0,
                  /*6 attention smem carveout %*/ 0, /*7 SIMT stem / tail convs*/ 0,
                   /*8 programmatic dependent launch of the GEMMs*/ 1,
-                  /*9 CUDA-graph replay of nb200_model_forward*/ 0, 0, 0, 0, 0, 0, 0};
+                  /*9 CUDA-graph replay of nb200_model_forward*/ 0,
+                  /*10 unfused Swin blocks (round-1 launch sequence)*/ 0, 0, 0, 0, 0, 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {
-    static int configured = 0;  // per instantiation: largest size configured so far
-    if ((int)smem > configured) {
-        NB_CUDA(cudaFuncSetAttribute(gemm_conv_persistent<BN, BK, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = (int)smem;
-    }
+    if (ensure_dyn_smem((const void*)gemm_conv_persistent<BN, BK, RES>, smem)) return 1;
     pp.stages = stages;
     // programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream drains (that kernel
     // must have executed griddepcontrol.launch_dependents); its prologue (barriers, TMEM, tensor-map prefetch, the static

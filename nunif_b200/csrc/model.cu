@@ -8,6 +8,7 @@
 #include "cunet_kernels.h"
 #include "depth_kernels.h"
 #include "rowflow_kernels.h"
+#include "swin_fused.h"
 #include "../../include/nunif_b200.h"
 #include <map>
 #include <vector>
@@ -186,7 +187,9 @@ static Lin pack_stem(Packer& pk, const std::string& name, int cout, int cout_pad
 
 struct SwinBlockW {
     Lin qkv, proj, fc1, fc2;
-    size_t table = 0;
+    Lin qkv_fused;        // rows regrouped per head pair for swin_fused_attn.cu
+    size_t table = 0;     // bias in accumulator-fragment order (unfused attention kernel)
+    size_t btab = 0;      // bias as [6][36][40] fp32 (fused attention kernel)
     int C = 0, shift = 0;
 };
 
@@ -275,6 +278,24 @@ static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std
         b.C = C;
         b.shift = (i % 2 == 0) ? 0 : 3;  // swin_unet.py:30
         b.qkv = pack_linear(pk, p + ".attn.qkv", 3 * C, C);
+        {   // the same Linear with rows ordered (head pair, {q,k,v}, head in pair, d): one N = 6d GEMM chunk per head pair
+            const float* w = pk.get(p + ".attn.qkv.weight", (int64_t)3 * C * C);
+            const float* bq = pk.get(p + ".attn.qkv.bias", 3 * C);
+            if (w && bq) {
+                const int D = C / 6;
+                std::vector<float> wv((size_t)3 * C * C), bv(3 * C);
+                for (int pr = 0; pr < 3 * C; ++pr) {
+                    const int c = pr / (6 * D), rem = pr % (6 * D);
+                    const int mm = rem / (2 * D), hh = (rem % (2 * D)) / D, d = rem % D;
+                    const int src = mm * C + (2 * c + hh) * D + d;
+                    memcpy(&wv[(size_t)pr * C], &w[(size_t)src * C], (size_t)C * 4);
+                    bv[pr] = bq[src];
+                }
+                b.qkv_fused.N = 3 * C; b.qkv_fused.K = C;
+                b.qkv_fused.w = pk.add_f16(wv);
+                b.qkv_fused.b = pk.add_f32(bv);
+            }
+        }
         b.proj = pack_linear(pk, p + ".attn.proj", C, C);
         b.fc1 = pack_linear(pk, p + ".mlp.0", 2 * C, C);
         b.fc2 = pack_linear(pk, p + ".mlp.3", C, 2 * C);
@@ -300,6 +321,15 @@ static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std
                                 frag[((((size_t)head * 3 + mt) * 6 + nt) * 32 + lane) * 4 + r] = v;
                             }
             b.table = pk.add_f32(frag);
+            // [head][36 queries][40 keys]: log2(e) * bias, key columns 36..39 masked (swin_fused_attn.cu)
+            std::vector<float> tab((size_t)6 * 36 * 40, -1e30f);
+            for (int head = 0; head < 6; ++head)
+                for (int row = 0; row < 36; ++row)
+                    for (int col = 0; col < 36; ++col) {
+                        const int qy = row / 6, qx = row % 6, ky = col / 6, kx = col % 6;
+                        tab[((size_t)head * 36 + row) * 40 + col] = 1.4426950408889634f * t[((qy - ky + 5) * 11 + (qx - kx + 5)) * 6 + head];
+                    }
+            b.btab = pk.add_f32(tab);
         }
         pk.mark(p + ".attn.relative_position_index");  // buffer; the kernel recomputes the index (swin_transformer.py:267-279)
         out.push_back(b);
@@ -363,7 +393,20 @@ static int swin_block(cudaStream_t st, const nb200_model* m, const SwinBlockW& w
                       __half* HID) {
     const int C = w.C;
     const long long T = (long long)n * H * H;
-    // q | k | v are written as three dense [T][C] planes: every CTA stores whole contiguous rows, and the
+    if (g_tune[10] == 0) {
+        // two launches per block (swin_fused_attn.cu, swin_fused_mlp.cu): q/k/v, x1 and the hidden tensor never reach HBM
+        FusedAttn fa;
+        fa.x = X; fa.att = ATT; fa.B = n; fa.H = H; fa.W = H; fa.C = C; fa.shift = w.shift;
+        fa.wqkv = m->at<__half>(w.qkv_fused.w); fa.bqkv = m->at<float>(w.qkv_fused.b); fa.bias_tab = m->at<float>(w.btab);
+        if (swin_attn_fused(st, fa)) return 1;
+        FusedMlp fm;
+        fm.x = X; fm.att = ATT; fm.T = T; fm.C = C;
+        fm.wp = m->at<__half>(w.proj.w); fm.bp = m->at<float>(w.proj.b);
+        fm.w1 = m->at<__half>(w.fc1.w); fm.b1 = m->at<float>(w.fc1.b);
+        fm.w2 = m->at<__half>(w.fc2.w); fm.b2 = m->at<float>(w.fc2.b);
+        return swin_mlp_fused(st, fm);
+    }
+    // unfused path (nb200_tune_set(10, 1); kept for A/B measurements).  q | k | v are written as three dense [T][C] planes: every CTA stores whole contiguous rows, and the
     // attention kernel reads each matrix with unit stride
     if (linear_flat(st, m, w.qkv, X, T, C, QKV, C, ACT_NONE, nullptr, 0, /*split=*/C)) return 1;
     if (window_attention(st, QKV, m->at<float>(w.table), ATT, n, H, H, C, w.shift, (size_t)T * C)) return 1;

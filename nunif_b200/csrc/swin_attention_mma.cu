@@ -16,6 +16,8 @@
 // right instrument here.
 #include "common.cuh"
 #include "swin_kernels.h"
+#include <map>
+#include <mutex>
 
 namespace nb200 {
 
@@ -297,6 +299,22 @@ static size_t attn_smem_bytes() {
     return (size_t)3 * WTOK * LD * 2 + (WTOK + WPAD) * 4 + 16;
 }
 
+// opt-in shared memory + carveout, per (device, kernel): both attributes are per-device state
+static int set_attn_attrs(const void* func, size_t smem, int carveout) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> done;
+    int dev = 0;
+    NB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    int& have = done[{dev, func}];
+    if (have != carveout) {
+        NB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        have = carveout;
+    }
+    return 0;
+}
+
 int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_f, __half* out, int B, int H, int W, int C,
                      int shift, size_t plane) {
     const float4* bias_table = reinterpret_cast<const float4*>(bias_frag_f);
@@ -308,22 +326,12 @@ int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag_
     // shared-memory carveout: just enough for the 4 resident CTAs, the rest stays L1 (the per-head bias fragments,
     // 55 KB per layer, are re-read by every window and should hit there).  g_tune[6] overrides the percentage.
     if (C == 96) {
-        static int cfg = -1;
         const int want = g_tune[6] > 0 ? g_tune[6] : 72;   // 6 CTAs x 23.6 KB
-        if (cfg != want) {
-            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<16>()));
-            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-            cfg = want;
-        }
+        if (set_attn_attrs((const void*)window_attention_mma_kernel<16>, attn_smem_bytes<16>(), want)) return 1;
         window_attention_mma_kernel<16><<<grid, 192, attn_smem_bytes<16>(), st>>>(qkv, bias_table, out, H, W, shift, plane);
     } else {
-        static int cfg = -1;
         const int want = g_tune[6] > 0 ? g_tune[6] : 86;
-        if (cfg != want) {
-            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<32>()));
-            NB_CUDA(cudaFuncSetAttribute(window_attention_mma_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-            cfg = want;
-        }
+        if (set_attn_attrs((const void*)window_attention_mma_kernel<32>, attn_smem_bytes<32>(), want)) return 1;
         window_attention_mma_kernel<32><<<grid, 192, attn_smem_bytes<32>(), st>>>(qkv, bias_table, out, H, W, shift, plane);
     }
     NB_LAUNCHED();

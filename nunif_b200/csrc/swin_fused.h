@@ -1,0 +1,35 @@
+// Fused Swin-block kernels (swin_fused_mlp.cu, swin_fused_attn.cu): two launches per SwinTransformerBlock.
+#pragma once
+#include "common.cuh"
+
+namespace nb200 {
+
+// x <- x1 + fc2(gelu(fc1(x1))),  x1 = x + att.Wp^T + bp  (att == nullptr: x1 = x).  x is [T][C] fp16, updated in place.
+struct FusedMlp {
+    __half* x = nullptr;
+    const __half* att = nullptr;
+    long long T = 0;
+    int C = 0;
+    const __half* wp = nullptr;   // [C][C]
+    const float* bp = nullptr;
+    const __half* w1 = nullptr;   // [2C][C]
+    const float* b1 = nullptr;
+    const __half* w2 = nullptr;   // [C][2C]
+    const float* b2 = nullptr;
+};
+int swin_mlp_fused(cudaStream_t st, const FusedMlp& f);
+
+// att <- window_attention(x.Wqkv^T + bqkv)  (everything of shifted_window_attention but the proj Linear).
+// x, att: [B][H][W][C] fp16; wqkv_packed: rows regrouped per head pair (pack_qkv_for_fused); bias_tab: [6][36][40] fp32
+// (log2e * relative position bias, columns 36..39 = -1e30).
+struct FusedAttn {
+    const __half* x = nullptr;
+    __half* att = nullptr;
+    int B = 0, H = 0, W = 0, C = 0, shift = 0;
+    const __half* wqkv = nullptr;   // [3C][C], row order (pair, {q,k,v}, head-in-pair, d)
+    const float* bqkv = nullptr;    // [3C], same order
+    const float* bias_tab = nullptr;
+};
+int swin_attn_fused(cudaStream_t st, const FusedAttn& f);
+
+}  // namespace nb200

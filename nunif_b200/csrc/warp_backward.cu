@@ -318,11 +318,7 @@ extern int g_tune[16];  // gemm.cu; [3] != 0 forces the gather-from-global kerne
 
 template <int COMPOSE>
 static int launch_bw_row(const BwParams& p, size_t smem, int S, int vec_ok, cudaStream_t st) {
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        NB_CUDA(cudaFuncSetAttribute(backward_warp_row_kernel<COMPOSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (ensure_dyn_smem((const void*)backward_warp_row_kernel<COMPOSE>, smem)) return 1;
     backward_warp_row_kernel<COMPOSE><<<dim3(p.H, p.B), 256, smem, st>>>(p, S, vec_ok);
     return 0;
 }

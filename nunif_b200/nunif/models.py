@@ -110,6 +110,8 @@ class B200I2IModel:
         """model(minibatch): x B,3,T,T float/half in [0,1] on self.device -> B,3,S,S fp16
         (what the reference returns under CUDA autocast)."""
         _lib.require_cuda(x, "x")
+        if x.device != self.device:
+            raise RuntimeError(f"input is on {x.device} but the model's packed weights live on {self.device}")
         assert x.ndim == 4 and x.shape[1] == 3 and x.shape[2] == x.shape[3]
         B, _, T, _ = x.shape
         xh = torch.zeros((B, T, T, 8), device=x.device, dtype=torch.float16)

@@ -10,6 +10,12 @@ import torch.nn.functional as F
 from .. import _lib
 
 
+def _require_amp(enable_amp):
+    if not enable_amp:
+        raise NotImplementedError("nunif_b200 implements the reference's CUDA autocast (fp16) forward only; "
+                                  "enable_amp=False (fp32 forward) is not implemented")
+
+
 class Waifu2x():
     def __init__(self, model_dir, gpus):
         self.scale_model = None
@@ -29,23 +35,48 @@ class Waifu2x():
         self.model_dir = model_dir
         self.is_half = False
 
-    # API parity no-ops: the engine is already ahead-of-time compiled fp16
     def compile(self):
+        """waifu2x/utils.py:49-58 wraps the modules in torch.compile; this engine's kernels are compiled ahead of time
+        (nvcc, sm_100a), so there is nothing left to do - same results either way, as in the reference."""
         return self
 
-    def warmup(self, *args, **kwargs):
+    def _loaded_models(self):
+        slots = [self.scale_model, self.scale4x_model, *self.noise_models, *self.noise_scale_models, *self.noise_scale4x_models]
+        return [m for m in slots if m is not None]
+
+    @torch.inference_mode()
+    def warmup(self, tile_size=None, batch_size=None, enable_amp=True):
+        """waifu2x/utils.py:60-83: one forward per loaded model and batch size, which here sizes the workspaces, sets the
+        per-device kernel attributes and loads the cubins before the first real frame."""
+        _require_amp(enable_amp)
+        for model in self._loaded_models():
+            t = model.i2i_default_tile_size if tile_size is None else model.find_valid_tile_size(tile_size)
+            n = model.i2i_default_batch_size if batch_size is None else batch_size
+            for bs in range(n, 0, -1):
+                model(torch.zeros((bs, 3, t, t), device=self.device, dtype=torch.float16 if self.is_half else torch.float32))
+        torch.cuda.synchronize(self.device)
         return self
 
     def to(self, device):
-        if torch.device(device).type != "cuda":
+        """The packed weights live on the device they were created on (one process per GPU); only a no-op move is possible."""
+        device = torch.device(device)
+        if device.type != "cuda":
             raise RuntimeError("nunif_b200 models cannot be moved to the CPU")
+        if device.index is not None and device != self.device and self._loaded_models():
+            raise RuntimeError(f"nunif_b200 models are bound to {self.device}; create a Waifu2x(gpus=[{device.index}]) instead")
+        if device.index is not None:
+            self.device = device
         return self
 
     def half(self):
+        """Reference: weights and inputs in fp16 (utils.py:90-93).  The engine's storage is fp16 already; this only
+        switches the tensors handed to / returned by ``model(x)`` and ``infer_pil`` to fp16."""
         self.is_half = True
         return self
 
     def float(self):
+        """Reference default state: fp32 weights run under CUDA autocast (nunif/device.py:58-71) - the numerics this engine
+        implements.  (An fp32 *forward*, ``enable_amp=False``, is not implemented and raises.)"""
         self.is_half = False
         return self
 
@@ -116,16 +147,18 @@ class Waifu2x():
         return self._slot(method, noise_level)
 
     @torch.inference_mode()
-    def render(self, x, method, noise_level, tile_size=None, batch_size=None, enable_amp=False):
-        """waifu2x/utils.py:218-241."""
+    def render(self, x, method, noise_level, tile_size=None, batch_size=None, enable_amp=True):
+        """waifu2x/utils.py:218-241.  (Reference default ``enable_amp=False``; the only implemented mode here is True.)"""
+        _require_amp(enable_amp)
         assert (method in ("scale", "noise_scale", "noise", "scale4x", "noise_scale4x"))
         assert (method in {"scale", "scale4x"} or 0 <= noise_level and noise_level < 4)
         return tiled_render(x, self._model(method, noise_level), tile_size=tile_size, batch_size=batch_size,
                             enable_amp=enable_amp)
 
     def convert(self, x, alpha, method, noise_level, tile_size=None, batch_size=None,
-                tta=False, enable_amp=False, output_device="cpu"):
-        """waifu2x/utils.py:255-297."""
+                tta=False, enable_amp=True, output_device="cpu"):
+        """waifu2x/utils.py:255-297.  (Reference default ``enable_amp=False``; the only implemented mode here is True.)"""
+        _require_amp(enable_amp)
         assert (not torch.is_grad_enabled())
         assert (x.shape[0] == 3)
         assert (alpha is None or alpha.shape[0] == 1 and alpha.shape[1:] == x.shape[1:])

@@ -1,0 +1,105 @@
+"""Time the fused Swin-block kernels against the unfused launch sequence at the bench shapes (16 tiles of 256^2).
+Usage (GPU box): python profiles/fused_bench.py [out.json]"""
+import json
+import sys
+import os
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nunif_b200 import _lib  # noqa: E402
+
+DEV = "cuda:0"
+L = _lib.lib()
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm(A, W, b, act, out, res=None, split=0):
+    M, K = A.shape[-2], A.shape[-1]
+    N = W.shape[0]
+    _lib.check(L.nb200_conv_gemm_f16(_lib.ptr(A), 1, 1, M, K, K, 0, _lib.ptr(W), N, _lib.ptr(b), act, _lib.ptr(out), out.shape[-1],
+                                     0, 0, _lib.ptr(res), res.shape[-1] if res is not None else 0, 0, 0, 0, 0, 0, _lib.stream_ptr()))
+
+
+def main():
+    out = {}
+    for T, C in [(921600, 192), (921600, 96), (230400, 192), (57600, 192)]:
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(T, C, generator=g).half().to(DEV)
+        att = torch.randn(T, C, generator=g).half().to(DEV)
+        wp = (torch.randn(C, C, generator=g) / C ** 0.5).half().to(DEV)
+        bp = torch.zeros(C, device=DEV)
+        w1 = (torch.randn(2 * C, C, generator=g) / C ** 0.5).half().to(DEV)
+        b1 = torch.zeros(2 * C, device=DEV)
+        w2 = (torch.randn(C, 2 * C, generator=g) / (2 * C) ** 0.5).half().to(DEV)
+        b2 = torch.zeros(C, device=DEV)
+        hid = torch.empty(T, 2 * C, dtype=torch.float16, device=DEV)
+
+        def fused():
+            _lib.check(L.nb200_swin_mlp_fused_f16(_lib.ptr(x), _lib.ptr(att), T, C, _lib.ptr(wp), _lib.ptr(bp), _lib.ptr(w1), _lib.ptr(b1),
+                                                  _lib.ptr(w2), _lib.ptr(b2), _lib.stream_ptr()))
+
+        def fused_noproj():
+            _lib.check(L.nb200_swin_mlp_fused_f16(_lib.ptr(x), None, T, C, _lib.ptr(wp), _lib.ptr(bp), _lib.ptr(w1), _lib.ptr(b1),
+                                                  _lib.ptr(w2), _lib.ptr(b2), _lib.stream_ptr()))
+
+        def unfused():
+            gemm(att, wp, bp, 0, x, res=x)
+            gemm(x, w1, b1, 2, hid)
+            gemm(hid, w2, b2, 0, x, res=x)
+
+        tf, tn, tu = timeit(fused), timeit(fused_noproj), timeit(unfused)
+        flop = 2.0 * T * C * C * 5
+        out[f"mlp_T{T}_C{C}"] = dict(fused_us=tf, fused_noproj_us=tn, unfused_us=tu, fused_tflops=flop / tf / 1e6,
+                                      hbm_floor_us=T * C * 2 * 3 / 6558e3)
+        print(f"mlp T={T} C={C}: fused {tf:.1f} us ({flop / tf / 1e6:.0f} TF/s), no-proj {tn:.1f} us, unfused {tu:.1f} us", flush=True)
+    for B, H, C in [(16, 240, 192), (16, 240, 96), (16, 120, 192), (16, 60, 192)]:
+        g = torch.Generator().manual_seed(2)
+        T = B * H * H
+        x = torch.randn(B, H, H, C, generator=g).half().to(DEV)
+        wqkv = (torch.randn(3 * C, C, generator=g) / C ** 0.5).half().to(DEV)
+        bqkv = torch.zeros(3 * C, device=DEV)
+        table = (0.5 * torch.randn(121, 6, generator=g)).to(DEV)
+        att = torch.empty(B, H, H, C, dtype=torch.float16, device=DEV)
+        qkv = torch.empty(3, T, C, dtype=torch.float16, device=DEV)
+        ws = [wqkv[i * C:(i + 1) * C].contiguous() for i in range(3)]
+        bs = [bqkv[i * C:(i + 1) * C].contiguous() for i in range(3)]
+
+        def fused_attn(shift=3):
+            _lib.check(L.nb200_swin_attn_fused_f16(_lib.ptr(x), _lib.ptr(wqkv), _lib.ptr(bqkv), _lib.ptr(table), _lib.ptr(att),
+                                                   B, H, H, C, shift, _lib.stream_ptr()))
+
+        def unfused_attn():
+            for i in range(3):
+                gemm(x.view(T, C), ws[i], bs[i], 0, qkv[i])
+            _lib.check(L.nb200_window_attention_f16(_lib.ptr(qkv), _lib.ptr(table), _lib.ptr(att), B, H, H, C, 6, 3, _lib.stream_ptr()))
+
+        tf, t0, tu = timeit(fused_attn), timeit(lambda: fused_attn(0)), timeit(unfused_attn)
+        flop = 2.0 * T * C * 3 * C + 4.0 * T * 36 * C
+        out[f"attn_B{B}_H{H}_C{C}"] = dict(fused_us=tf, fused_shift0_us=t0, unfused_us=tu, fused_tflops=flop / tf / 1e6,
+                                            hbm_floor_us=T * C * 2 * 2 / 6558e3)
+        print(f"attn B={B} H={H} C={C}: fused {tf:.1f} us ({flop / tf / 1e6:.0f} TF/s; includes 2 small pack kernels), shift0 {t0:.1f}, "
+              f"unfused(3 GEMMs + attention) {tu:.1f} us", flush=True)
+    if len(sys.argv) > 1:
+        with open(sys.argv[1], "w") as fh:
+            json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
