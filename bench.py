@@ -97,51 +97,142 @@ def cpu_reference_sample(n_tiles, threads):
         return time.perf_counter() - t0
 
 
-def pick_cpu_threads(cores):
-    """torch-CPU on many-core hosts is often slower with every core than with a few dozen threads (small per-tile GEMMs,
-    barrier cost, NUMA).  Time one tile at a few thread counts and use the fastest, so that the CPU arm is the best the host
-    can do rather than an oversubscribed one.  Returns (threads, {threads: seconds})."""
-    cands = sorted({c for c in (cores, 64, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
-    timings = {}
-    for c in cands:
-        cpu_reference_sample(1, c)                       # warm (allocator, oneDNN primitives)
-        timings[c] = cpu_reference_sample(1, c)
-    best = min(timings, key=timings.get)
-    return best, {str(k): round(v, 3) for k, v in timings.items()}
+def cpu_worker_main(n_tiles, threads):
+    """`bench.py --cpu-worker N T`: one tile batch on T threads; prints wall-clock start / end (time.time) as JSON."""
+    import torch
+    from nunif_b200 import synth
+    from oracle import swin_unet as osw
+    torch.set_num_threads(threads)
+    sd = synth.swin_unet_state_dict(0, 4)
+    x = torch.stack([synth.synth_image(100 + i, 3, TILE, TILE) for i in range(n_tiles)])
+    with torch.inference_mode():
+        osw.swin_unet_forward(sd, x[:1, :, :64, :64].contiguous(), 4)     # warm: allocator, oneDNN primitives
+        t0 = time.time()
+        osw.swin_unet_forward(sd, x, 4)
+        t1 = time.time()
+    print(json.dumps({"t0": t0, "t1": t1}), flush=True)
 
 
-def frame_tiles(h, w):
-    from oracle import seam_blending as osb
-    cfg = osb.create_config(h, w, 4, 32, TILE, 16)
+def cpu_reference_concurrent(workers, tiles_per_worker, threads):
+    """`workers` processes, each pushing one batch of `tiles_per_worker` tiles through the model on `threads` threads at the
+    same time - how a CPU run of the reference keeps a many-core host busy (one torch process scales poorly past a few dozen
+    threads on the small per-tile GEMMs).  Returns (seconds from the first start to the last finish, tiles done)."""
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", str(tiles_per_worker), str(threads)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                              env={**os.environ, "OMP_NUM_THREADS": str(threads), "MKL_NUM_THREADS": str(threads)})
+             for _ in range(workers)]
+    spans = []
+    for pr in procs:
+        out, _ = pr.communicate()
+        lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+        if pr.returncode == 0 and lines:
+            spans.append(json.loads(lines[-1]))
+    if not spans:
+        raise RuntimeError("CPU reference workers failed")
+    return max(sp["t1"] for sp in spans) - min(sp["t0"] for sp in spans), len(spans) * tiles_per_worker
+
+
+def cpu_plan(cores):
+    """(workers, threads per worker): at least 8 concurrent tile batches, every core used."""
+    workers = 8 if cores >= 16 else max(1, cores // 2)
+    return workers, max(1, cores // workers)
+
+
+def frame_tiles(h, w, scale=4, offset=32, blend=16):
+    """Tiles per frame from the library's host integer planner (nb200_tile_config_create == SeamBlending.create_config)."""
+    from nunif_b200.nunif.render import create_config
+    cfg = create_config((h, w), scale, offset, TILE, blend)
     return cfg["h_blocks"] * cfg["w_blocks"]
 
 
+def cpu_baseline_object(h, w, ntiles, tiles_per_worker=1):
+    cores = host_cores()
+    workers, threads = cpu_plan(cores)
+    t, done = cpu_reference_concurrent(workers, tiles_per_worker, threads)
+    mp = h * w / 1e6
+    val = mp * done / ntiles / t
+    return t, {"value": val, "unit": "MP/s", "cores": workers * threads, "kind": "port", "host_cores": cores,
+               "workers": workers, "threads_per_worker": threads,
+               "sample": f"{done} of the {ntiles} 256x256 tiles of one frame: {workers} concurrent processes x {tiles_per_worker} tile(s) "
+                         f"through oracle/swin_unet.py (torch-CPU fp32, {threads} threads each), {t:.1f} s wall from first start "
+                         f"to last finish; MP/s = frame MP * {done}/{ntiles} / t"}
+
+
 def run_reference(args):
+    """The reference arm: the reference's algorithm (oracle port; the reference itself is Python with no installable package
+    and cannot travel to the GPU box) on ALL host cores - several tile batches at a time, every core busy."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     h, w = FRAME[args.frame]
     ntiles = frame_tiles(h, w)
-    cores, thread_sweep = pick_cpu_threads(host_cores())
-    sample_tiles = 2
-    mp_per_step = (h * w / 1e6) * sample_tiles / ntiles
-    ts = [cpu_reference_sample(sample_tiles, cores) for _ in range(args.steps)]
-    t = sum(ts) / len(ts)
-    val = mp_per_step / t
+    ts, cb = [], None
+    for _ in range(max(1, args.steps)):
+        t, cb = cpu_baseline_object(h, w, ntiles)
+        ts.append((t, cb["value"]))
+    val = sum(v for _, v in ts) / len(ts)
+    t = sum(tt for tt, _ in ts) / len(ts)
+    cb["value"] = val
     line = {
         "impl": "reference", "metric": "waifu2x_input_megapixels_per_sec", "value": val, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} input 3x{h}x{w}, tile_size=256 batch=16, "
-                               f"{ntiles} tiles/frame, 1 frame/GPU/step"},
-        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port", "host_cores": host_cores(),
-                         "thread_sweep_seconds_per_tile": thread_sweep,
-                         "sample": f"{sample_tiles} of the {ntiles} 256x256 tiles of one {args.frame} frame per step, "
-                                   f"oracle/swin_unet.py on torch-CPU fp32 with the fastest thread count of the sweep; "
-                                   f"MP/s = frame MP * {sample_tiles}/{ntiles} / t"},
+                               f"{ntiles} tiles/frame, 1 frame/GPU/step",
+                   "warmup_note": "each worker warms its allocator / oneDNN primitives on a 64x64 tile before its timed batch"},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_torch_gpu(args):
+    """`--impl torch_gpu`: what the reference itself does on a CUDA device - its PyTorch modules (oracle restatement, same ops)
+    under torch.autocast(fp16) (nunif/device.py:58-71), eager or torch.compile'd (waifu2x/utils.py:25-39 `compile`), through
+    the reference's tiling loop (oracle/seam_blending.py) with the frame resident in HBM.  Same metric and workload as the
+    default arm; a BASELINE only (SURVEY 8d / BASELINE.md section 3), never part of the product path."""
+    import torch
+    from nunif_b200 import synth
+    from oracle import swin_unet as osw, seam_blending as osb
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    h, w = FRAME[args.frame]
+    ntiles = frame_tiles(h, w)
+    sd = {k: v.to(dev) for k, v in synth.swin_unet_state_dict(0, 4).items()}
+    x = synth.synth_image(1000, 3, h, w, smooth=False).to(dev)
+
+    def fwd(b):
+        return osw.swin_unet_forward(sd, b, 4)
+    model = torch.compile(fwd) if args.compile else fwd
+
+    def amp_model(b):
+        with torch.autocast("cuda", dtype=torch.float16):
+            return model(b.to(dev))
+
+    def step():
+        return osb.tiled_render(x, amp_model, 4, 32, 16, TILE, BATCH)
+    with torch.no_grad():
+        for _ in range(max(1, args.warmup)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(dev.index or 0) as clocks:
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    val = args.steps * (h * w / 1e6) / (ms / 1e3)
+    print(json.dumps({
+        "impl": "torch_gpu", "metric": "waifu2x_input_megapixels_per_sec", "value": val, "unit": "MP/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "clocks": clocks.summary(),
+        "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} input 3x{h}x{w}, tile_size=256 batch=16, {ntiles} tiles/frame",
+                   "engine": "PyTorch " + torch.__version__ + (" torch.compile" if args.compile else " eager") + ", torch.autocast(fp16)",
+                   "frames_per_sec": args.steps / (ms / 1e3)}}), flush=True)
 
 
 def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
@@ -427,13 +518,35 @@ def run_b200(args):
     value = world * args.steps * mp / (ms / 1e3)
     e2e = world * e2e_steps * mp / (ms_e2e / 1e3)
     peaks, peak_src = load_peaks()
-    gemm = prof.get("gemm", {"launches": 0, "ms": 0.0, "work": 0.0, "hbm_bytes": 0.0, "hbm_floor_ms": 0.0})
-    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    ach = gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] > 0 else 0.0
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])     # kernels timed inside a long step: the sustained figure
     total_prof_ms = sum(v["ms"] for v in prof.values())
-    attn = prof.get("window_attention", {"launches": 0, "ms": 0.0, "work": 0.0, "hbm_bytes": 0.0, "hbm_floor_ms": 0.0})
-    gemm_gbs = gemm.get("hbm_bytes", 0.0) / (gemm["ms"] / 1e3) / 1e9 if gemm["ms"] > 0 else 0.0
-    attn_gbs = attn.get("hbm_bytes", 0.0) / (attn["ms"] / 1e3) / 1e9 if attn["ms"] > 0 else 0.0
+    KERNEL_OF = {"fused_attn": "swin_attn_fused_kernel (tcgen05 qkv GEMM + window attention, q/k/v in shared memory)",
+                 "fused_mlp": "swin_mlp_fused2_kernel / swin_mlp_fused_kernel (tcgen05 [proj +] fc1 + GELU + fc2, hidden in smem/TMEM)",
+                 "gemm": "gemm_conv_persistent (tcgen05 implicit GEMM: convs, patch up/down, proj of the C=192 blocks, to_image)"}
+
+    def tensor_view(name):
+        c = prof.get(name)
+        if not c or c["ms"] <= 0:
+            return None
+        tf = c["work"] / (c["ms"] / 1e3) / 1e12
+        gbs = c.get("hbm_bytes", 0.0) / (c["ms"] / 1e3) / 1e9
+        return {"kernel": KERNEL_OF[name], "tflops": tf, "tensor_frac": tf / peak_tf, "launches": c["launches"],
+                "avg_launch_us": c["ms"] * 1e3 / max(1, c["launches"]), "ms_per_frame": c["ms"],
+                "share_of_step": c["ms"] / total_prof_ms if total_prof_ms else None,
+                "hbm_GBps_algorithmic": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
+                "flop_per_launch": c["work"] / max(1, c["launches"]), "hbm_bytes_per_launch": c.get("hbm_bytes", 0.0) / max(1, c["launches"])}
+    views = {k: tensor_view(k) for k in KERNEL_OF}
+    views = {k: v for k, v in views.items() if v}
+    dom = max(views, key=lambda k: views[k]["ms_per_frame"]) if views else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of the shipped kernels, parsed from an ncu --set full capture by
+    # profiles/ncu_traffic.py into profiles/r2/ncu_traffic.json (per launch of the largest launch class); null until captured
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r2", "ncu_traffic.json")
+    if dom and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except (OSError, ValueError):
+            traffic = None
     line = {
         "metric": "waifu2x_input_megapixels_per_sec", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -451,23 +564,18 @@ def run_b200(args):
                         "of finished tile rows on a side stream) -> pinned host fp32 output; every step moves all bytes"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "gemm_conv_persistent (tcgen05 implicit GEMM; all GEMM launches of one frame)",
-                     "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
-                     "peak_source": f"{peak_src} MEASURED_PEAKS.json hbm_gbs (copy)",
-                     "note": "Swin Linears have 96-144 FLOP/B < the 210 FLOP/B ridge: HBM-bound. achieved = algorithmic bytes "
-                             "(activations in + residual + out, weights once) / event time over all GEMM launches of the profiled frame. "
-                             "Streaming kernels on this pool reach 6.7-7.4 TB/s for any read:write mix and the GEMM's own TMA box "
-                             "pattern 6.0 (store) / 6.9 (load) TB/s without math (profiles/r1/hbm_mix.json, tma_pattern.json)",
-                     "tensor_tflops": ach, "tensor_peak_tflops": peak_tf, "tensor_frac": ach / peak_tf if peak_tf else None,
-                     "launches": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["launches"]),
-                     "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None,
-                     # ncu --set full of the largest launch class (qkv Linear of a 16-tile batch, M=921600 K=192 N=576):
-                     # dram__bytes_read.sum + dram__bytes_write.sum = 354.2 MB + 1003.3 MB against 1415.7 MB algorithmic,
-                     # i.e. no re-reads (profiles/r1/gemm_persistent_v1_qkv_ncu_full_summary.csv)
-                     "traffic": 1.3575e9, "traffic_algorithmic": 1.4157e9},
-        "roofline_attention": {"bound": "hbm", "kernel": "window_attention_mma_kernel", "achieved": attn_gbs, "peak": peaks["hbm_gbs"],
-                               "unit": "GB/s", "frac": attn_gbs / peaks["hbm_gbs"],
-                               "share_of_step": attn["ms"] / total_prof_ms if total_prof_ms else None},
+        "roofline": ({"bound": "tensor", "kernel": views[dom]["kernel"], "class": dom,
+                      "achieved": views[dom]["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": views[dom]["tensor_frac"],
+                      "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)",
+                      "launches": views[dom]["launches"], "avg_launch_us": views[dom]["avg_launch_us"],
+                      "share_of_step": views[dom]["share_of_step"],
+                      "note": "SURVEY 8(d): path A is judged against the tensor roofline.  achieved = algorithmic FLOPs of every launch of "
+                              "the dominant kernel class in one frame (2*M*N*K of its GEMMs + 4*T*36*C for QK^T/PV) / their CUDA-event "
+                              "time (nb200_profile_report, events on the launching stream)",
+                      "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                      "traffic_launch": (traffic or {}).get("launch"),
+                      "traffic_algorithmic": (traffic or {}).get("algorithmic_bytes_per_launch")} if dom else None),
+        "roofline_by_class": views,
         "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }
     if upc is not None:
@@ -478,14 +586,7 @@ def run_b200(args):
         line["iw3_1080p"] = iw3
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            cores, thread_sweep = pick_cpu_threads(host_cores())
-            sample_tiles = 2
-            tcpu = cpu_reference_sample(sample_tiles, cores)
-            line["cpu_baseline"] = {
-                "value": mp * sample_tiles / ntiles / tcpu, "unit": "MP/s", "cores": cores, "kind": "port",
-                "host_cores": host_cores(), "thread_sweep_seconds_per_tile": thread_sweep,
-                "sample": f"{sample_tiles} of {ntiles} tiles (256x256) of the same frame through oracle/swin_unet.py, torch-CPU fp32, "
-                          f"{tcpu:.2f} s; MP/s = frame MP * {sample_tiles}/{ntiles} / t"}
+            line["cpu_baseline"] = guarded(lambda: cpu_baseline_object(h, w, ntiles)[1])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -496,12 +597,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    ap.add_argument("--compile", action="store_true", help="--impl torch_gpu: wrap the forward in torch.compile")
+    ap.add_argument("--cpu-worker", nargs=2, type=int, metavar=("TILES", "THREADS"), help=argparse.SUPPRESS)
     ap.add_argument("--frame", default="4k", choices=list(FRAME))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.cpu_worker:
+        cpu_worker_main(*args.cpu_worker)
+    elif args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_b200(args)
 

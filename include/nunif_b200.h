@@ -104,8 +104,9 @@ int nb200_model_weight_blob(nb200_model* m, void** dev_ptr, size_t* bytes);
 
 /* model(minibatch) of seam_blending.py:94-95 under autocast fp16:
  * x: NHWC fp16 [n][T][T][8] (from nb200_tile_unfold, channels 3..7 zero)
- * z: planar fp16 [n][3][S][S], S = T*unet_scale/downscale - 2*offset (the reference's
- *    model output is fp16 under autocast as well).
+ * z: planar [n][3][S][S], S = T*unet_scale/downscale - 2*offset; fp16 for downscale == 1 (the reference's model
+ *    output is fp16 under autocast as well), fp32 for downscale 2 | 4 (SwinUNetDownscaled resizes z.float() and
+ *    returns fp32, waifu2x/models/swin_unet.py:366-379).
  * downscale in {1,2,4}: 2/4 apply SwinUNetDownscaled (swin_unet.py:366-379). */
 int nb200_model_forward(nb200_model* m, const void* x_nhwc_f16, int n, int tile_size,
                         int downscale, void* z_f16, void* stream);
@@ -194,6 +195,24 @@ int nb200_dilate_edge(const float* x, int B, int h, int w, int x_iter, int y_ite
 int nb200_minmax_map(const float* depth, int B, int n_per_frame, float mapper_c,
                      float* out, float* minmax_out /* [B][2] or NULL */, void* stream);
 
+/* Stateful depth normaliser: MinMaxBuffer + EMAMinMaxScaler (iw3/depth_scaler.py:33-142; BaseDepthModel.enable_ema /
+ * minmax_normalize_chw / flush_minmax_normalize, iw3/base_depth_model.py:152-194).  All values stay on the device; the
+ * host only counts calls, so a frame costs three small launches and no synchronisation (csrc/ema_scaler.cu).
+ * mode: 0 = "minmax", 1 = "max".  reset: decay < 0 / buffer_size <= 0 keep the current value (:76-86).
+ * update: pushes the frame's amin/amax, *filled = the look-ahead buffer is full, i.e. the OLDEST queued frame can now be
+ *   normalised (the frame queue itself lives with the caller).
+ * normalize: from_ring = 0 uses the EMA values (:108-116), 1 the ring's amin/amax (flush before a value exists, :127-128);
+ *   mapper_c >= 0 applies distance_to_disparity(x, mapper_c) afterwards; minmax_out: optional 2 floats on the device. */
+typedef struct nb200_ema_scaler nb200_ema_scaler;
+int nb200_ema_scaler_create(int buffer_size, double decay, int mode, nb200_ema_scaler** out);
+void nb200_ema_scaler_destroy(nb200_ema_scaler* s);
+int nb200_ema_scaler_reset(nb200_ema_scaler* s, double decay, int buffer_size);
+int nb200_ema_scaler_update(nb200_ema_scaler* s, const float* frame, int n, int* filled, void* stream);
+int nb200_ema_scaler_normalize(nb200_ema_scaler* s, const float* frame, int n, int from_ring,
+                               float mapper_c, float* out, float* minmax_out, void* stream);
+/* iw3/mapper.py:29-32 get_mapper("div_*") alone: distance_to_disparity(x, mapper_c); in place allowed. */
+int nb200_depth_mapper(const float* depth, long long n, float mapper_c, float* out, void* stream);
+
 /* iw3/anaglyph.py:51-92 on already-warped eyes: l,r,out [B][3][H][W] */
 int nb200_anaglyph_dubois(const float* l, const float* r, int B, int H, int W, int clip_before,
                           float* out, void* stream);
@@ -273,6 +292,12 @@ int nb200_anaglyph(const float* l, const float* r, int B, int H, int W, int type
  * max-output-size resize of postprocess_image, iw3/utils.py:445-485); clamp01_out applies the following clamp. */
 int nb200_resize_bicubic_aa(const float* x, int planes, int H, int W, int oh, int ow, int clamp01_out,
                             float* out, void* stream);
+
+/* VR180 output (iw3/equirectangular.py:7-40; iw3/utils.py:441-443): zero-pad to 1.5 x the longer edge, bicubic grid_sample
+ * (zeros, align_corners=True) through x' = k tan(az), y' = k tan(el)/cos(az), clamp [0,1].
+ * c [C][H][W] -> out [C][out_h][out_w] with (out_h, out_w) from nb200_equirectangular_size (host rule). */
+int nb200_equirectangular_size(int H, int W, int* out_h, int* out_w);
+int nb200_equirectangular(const float* c, int C, int H, int W, float* out, void* stream);
 
 /* Kernel-class device timing (CUDA events around every launch of this library) used by
  * bench.py for the live roofline figure.  report writes a JSON object

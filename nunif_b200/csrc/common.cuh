@@ -60,7 +60,7 @@ struct ProfScope {
 };
 
 // seam_blend.cu: rows [y0, y1) of the blended output (used by the band-pipelined host render in model.cu)
-int tile_gather_blend_rows(const void* z_all, int C, const ::nb200_tile_config* cfg, int scale, int offset, int tile_size,
+int tile_gather_blend_rows(const void* z_all, int z_f32, int C, const ::nb200_tile_config* cfg, int scale, int offset, int tile_size,
                            int blend_size, float* out, int y0, int y1, void* stream);
 
 // Programmatic dependent launch (sm_90+): a kernel that executes this lets a PDL-attributed successor (the persistent

@@ -28,7 +28,11 @@ namespace nb200 {
 constexpr int PG_MAX_STAGES = 8;   // A(/B) ring depth upper bound
 constexpr int PG_MAX_QUADS = 4;    // epilogue quads (each 4 warps)
 constexpr int PG_EPI_WARPS = 4 * PG_MAX_QUADS;
-constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
+// TMA producers: warp 0 and the warps after the epilogue quads.  Bulk-tensor ops issued by ONE warp execute strictly one after
+// the other on this part (~0.34 us per op whatever its size), ops of different warps overlap (profiles/r2/tma_inflight.json):
+// the op sequence of a CTA is dealt round-robin to PG_PRODUCERS warps.  (3 producers = 640 threads keep 96 registers/thread.)
+constexpr int PG_PRODUCERS = 3;
+constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS + 32 * (PG_PRODUCERS - 1);
 
 struct PersistParams {
     GemmParams g;
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             mbar_init(&res_full[s], 1);
             mbar_init(&res_empty[s], 1);
         }
-        mbar_init(b_full, 1);
+        mbar_init(b_full, (uint32_t)k_iters);          // one arrival per resident weight chunk op
         fence_barrier_init();
     }
     if (threadIdx.x == 0) NB_PDL_TRIGGER();   // the next GEMM of the stream may start its prologue while this grid drains
@@ -132,43 +136,56 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer (one thread) =====================
+    if (warp == 0 || warp >= 2 + PG_EPI_WARPS) {
+        // ===================== TMA producers (one thread in each of PG_PRODUCERS warps) =====================
+        // Fixed ownership: mbarrier waits are 1-bit phase parities, so a thread must see EVERY phase of a barrier it waits on -
+        // activation ring slot s is always refilled by producer s % PG_PRODUCERS, residual slot rq by producer rq % PG_PRODUCERS.
+        // All producers walk the same op sequence, so slots and phases need no communication; every op does its own
+        // arrive.expect_tx on its barrier.
+        const int pid = warp == 0 ? 0 : warp - (2 + PG_EPI_WARPS) + 1;
         if (elect_one() && my_tiles > 0) {
             if (RESIDENT_B) {
-                mbar_expect_tx(b_full, (uint32_t)(k_iters * Cfg::B_BYTES));
-                for (int it = 0; it < k_iters; ++it) tma_load_2d(&maps.b, b_full, sB + it * B_BYTES, it * BK, n0);
+                for (int it = pid; it < k_iters; it += PG_PRODUCERS) {
+                    mbar_expect_tx(b_full, (uint32_t)Cfg::B_BYTES);
+                    tma_load_2d(&maps.b, b_full, sB + it * B_BYTES, it * BK, n0);
+                }
             }
             // everything above touched only launch constants (weights, bias, tensor maps); activations and residuals are
             // produced by the preceding kernels of the stream
             asm volatile("griddepcontrol.wait;" ::: "memory");
             TileWalk tw;
             tw.init(m_first, pp.grid_m, p.tiles_x, p.tiles_y);
-            int s = 0, rq = 0;
+            int s = 0, sown = 0, rq = 0, rown = 0;
             uint32_t ph = 0, rph = 0;
             for (int j = 0; j < my_tiles; ++j) {
                 const int x0 = tw.tx * p.TW, y0 = tw.ty * p.TH, b = tw.b;
                 int tap = 0, ch = 0;
                 for (int it = 0; it < k_iters; ++it) {
-                    mbar_wait(&a_empty[s], ph ^ 1);
-                    TL(0, 1);
-                    uint8_t* sa = sRing + s * STAGE_BYTES;
-                    mbar_expect_tx(&a_full[s], RESIDENT_B ? A_BYTES : A_BYTES + Cfg::B_BYTES);
-                    tma_load_5d(&maps.a, &a_full[s], sa, ch * BK, x0 + p.tap_dx[tap], p.tap_dyi[tap], y0 + p.tap_dy[tap], b);
-                    if (!RESIDENT_B) tma_load_2d(&maps.b, &a_full[s], sa + A_BYTES, it * BK, n0);
+                    if (sown == pid) {
+                        uint8_t* sa = sRing + s * STAGE_BYTES;
+                        mbar_wait(&a_empty[s], ph ^ 1);
+                        TL(0, 1);
+                        mbar_expect_tx(&a_full[s], RESIDENT_B ? A_BYTES : A_BYTES + Cfg::B_BYTES);
+                        tma_load_5d(&maps.a, &a_full[s], sa, ch * BK, x0 + p.tap_dx[tap], p.tap_dyi[tap], y0 + p.tap_dy[tap], b);
+                        if (!RESIDENT_B) tma_load_2d(&maps.b, &a_full[s], sa + A_BYTES, it * BK, n0);
+                    }
                     if (++ch == p.cpt) { ch = 0; ++tap; }
-                    if (++s == SA) { s = 0; ph ^= 1; }
+                    if (++sown == PG_PRODUCERS) sown = 0;
+                    if (++s == SA) { s = 0; sown = 0; ph ^= 1; }
                 }
                 if (p.has_res) {
                     // residual chunks of this tile, prefetched into the consuming quad's buffer NQ chunks ahead
                     int n = n0;
                     for (int c = 0; c < NCH; ++c, n += CW) {
-                        mbar_wait(&res_empty[rq], rph ^ 1);
-                        int g = 0, co = n;
-                        if (p.out_mode != OUT_NHWC) { g = n / p.cout; co = n - g * p.cout; }
-                        mbar_expect_tx(&res_full[rq], CH_BYTES);
-                        tma_load_4d(&maps.r[g], &res_full[rq], sRes + rq * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
-                        if (++rq == NQ) { rq = 0; rph ^= 1; }
+                        if (rown == pid) {
+                            mbar_wait(&res_empty[rq], rph ^ 1);
+                            int g = 0, co = n;
+                            if (p.out_mode != OUT_NHWC) { g = n / p.cout; co = n - g * p.cout; }
+                            mbar_expect_tx(&res_full[rq], CH_BYTES);
+                            tma_load_4d(&maps.r[g], &res_full[rq], sRes + rq * CH_BYTES, co, x0 + p.res_cx, y0 + p.res_cy, b);
+                        }
+                        if (++rown == PG_PRODUCERS) rown = 0;
+                        if (++rq == NQ) { rq = 0; rown = 0; rph ^= 1; }
                     }
                 }
                 tw.step();
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
                 if (++s == SA) { s = 0; ph ^= 1; }
             }
         }
-    } else {
+    } else if (warp < 2 + PG_EPI_WARPS) {
         // ===================== epilogue quads (warps 2..17) =====================
         const int quad = (warp - 2) >> 2;     // 0..3
         const int lane_grp = warp & 3;        // TMEM lanes [32*lane_grp, +32)
@@ -310,8 +327,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) gemm_conv_persistent(const __gr
             }
             if (qleader) tma_store_wait_read();
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();

@@ -188,6 +188,7 @@ static Lin pack_stem(Packer& pk, const std::string& name, int cout, int cout_pad
 struct SwinBlockW {
     Lin qkv, proj, fc1, fc2;
     Lin qkv_fused;        // rows regrouped per head pair for swin_fused_attn.cu
+    size_t fc1_cm = 0, proj_cm = 0;   // chunk-major [K/BK][rows][BK] fp16 copies for swin_fused_mlp2.cu
     size_t table = 0;     // bias in accumulator-fragment order (unfused attention kernel)
     size_t btab = 0;      // bias as [6][36][40] fp32 (fused attention kernel)
     int C = 0, shift = 0;
@@ -299,6 +300,19 @@ static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std
         b.proj = pack_linear(pk, p + ".attn.proj", C, C);
         b.fc1 = pack_linear(pk, p + ".mlp.0", 2 * C, C);
         b.fc2 = pack_linear(pk, p + ".mlp.3", C, 2 * C);
+        {   // chunk-major copies: all K-chunks of one GEMM chunk arrive with a single 3-D TMA box
+            const int bk = C == 192 ? 64 : 32;
+            auto cm = [&](const std::string& name, int rows, int K) -> size_t {
+                const float* w = pk.get(name, (int64_t)rows * K);
+                if (!w) return 0;
+                std::vector<float> v((size_t)rows * K);
+                for (int r = 0; r < rows; ++r)
+                    for (int k = 0; k < K; ++k) v[((size_t)(k / bk) * rows + r) * bk + (k % bk)] = w[(size_t)r * K + k];
+                return pk.add_f16(v);
+            };
+            b.fc1_cm = cm(p + ".mlp.0.weight", 2 * C, C);
+            b.proj_cm = cm(p + ".attn.proj.weight", C, C);
+        }
         const float* t = pk.get(p + ".attn.relative_position_bias_table", 121 * 6);
         if (t) {
             // relative-position bias expanded once into the attention kernel's accumulator-fragment order
@@ -404,7 +418,15 @@ static int swin_block(cudaStream_t st, const nb200_model* m, const SwinBlockW& w
         fm.wp = m->at<__half>(w.proj.w); fm.bp = m->at<float>(w.proj.b);
         fm.w1 = m->at<__half>(w.fc1.w); fm.b1 = m->at<float>(w.fc1.b);
         fm.w2 = m->at<__half>(w.fc2.w); fm.b2 = m->at<float>(w.fc2.b);
-        return swin_mlp_fused(st, fm);
+        fm.w1_cm = m->at<__half>(w.fc1_cm); fm.wp_cm = m->at<__half>(w.proj_cm);
+        if (g_tune[11]) return swin_mlp_fused(st, fm);        // one CTA per SM, proj fused (A/B)
+        // half-SM kernels, two CTAs per SM (swin_fused_mlp2.cu).  C = 192 has no shared memory for the att tile next to a
+        // second CTA: its proj Linear (+ residual) runs on the persistent GEMM and the MLP kernel starts from x1.
+        if (C == 192) {
+            if (linear_flat(st, m, w.proj, ATT, T, C, X, C, ACT_NONE, X, C)) return 1;    // x = x + attn(x)   :453
+            fm.att = nullptr;
+        }
+        return swin_mlp_fused2(st, fm);
     }
     // unfused path (nb200_tune_set(10, 1); kept for A/B measurements).  q | k | v are written as three dense [T][C] planes: every CTA stores whole contiguous rows, and the
     // attention kernel reads each matrix with unit stride
@@ -441,7 +463,7 @@ static size_t swin_ws_bytes(const SwinW& w, int n, int T) {
     return b + 4096;
 }
 
-static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n, int T, int down, __half* z) {
+static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n, int T, int down, void* z) {
     const SwinW& w = m->sw;
     NB_CHECK(T > 16 && (T - 16) % 12 == 0 && (T - 16) % 16 == 0, "invalid tile size for swin_unet (swin_unet.py:202-205)");
     const int C = w.C, Hc = T - 16, H2 = Hc / 2, H3 = Hc / 4, S1w = T - 2;
@@ -616,7 +638,7 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
     cudaStream_t st = (cudaStream_t)stream;
     NB_CHECK(m->kind <= NB200_MODEL_SWIN_UNET_4X, "not an image-to-image model");
     auto eager = [&]() {
-        if (m->kind >= NB200_MODEL_SWIN_UNET_1X) return swin_forward(m, st, (const __half*)x, n, tile_size, downscale, (__half*)z);
+        if (m->kind >= NB200_MODEL_SWIN_UNET_1X) return swin_forward(m, st, (const __half*)x, n, tile_size, downscale, z);
         return cunet_forward(m, st, (const __half*)x, n, tile_size, (__half*)z);
     };
     // CUDA graphs (g_tune[9]): the ~80 launches of one tile batch are replayed as one graph launch once the same
@@ -671,15 +693,18 @@ extern "C" int nb200_tiled_render(nb200_model* m, const float* x, int C, int H, 
     // frame-level buffers: the unfolded tile batch and every tile's output (persistent per model; not re-entrant:
     // one render at a time per model handle, like the reference's module)
     const size_t xb_elems = (size_t)batch_size * tile_size * tile_size * 8, z_tile = (size_t)3 * S * S;
-    if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * 2)) return 1;
-    __half *xb = m->frame_xb, *zall = m->frame_z;
+    const int z_f32 = downscale > 1;                      // the downscaled models return fp32 tiles (swin_unet.py:366-379)
+    const size_t zsz = z_f32 ? 4 : 2;
+    if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * zsz)) return 1;
+    __half* xb = m->frame_xb;
+    uint8_t* zall = reinterpret_cast<uint8_t*>(m->frame_z);
     int rc = 0;
     for (int t0 = 0; t0 < ntiles && !rc; t0 += batch_size) {
         const int nb = ntiles - t0 < batch_size ? ntiles - t0 : batch_size;
         rc = nb200_tile_unfold(x, C, H, W, &cfg, tile_size, t0, nb, xb, 8, stream);
-        if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile, stream);
+        if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile * zsz, stream);
     }
-    if (!rc) rc = nb200_tile_gather_blend(zall, C, &cfg, scale, offset, tile_size, blend, out, stream);
+    if (!rc) rc = tile_gather_blend_rows(zall, z_f32, C, &cfg, scale, offset, tile_size, blend, out, 0, cfg.y_h, stream);
     return rc;
 }
 
@@ -700,27 +725,30 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     if (!m->copy_stream) NB_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     cudaStream_t cs = m->copy_stream;
     const int ntiles = cfg.h_blocks * cfg.w_blocks;
-    __half *xb = nullptr, *zall = nullptr;
+    __half* xb = nullptr;
+    uint8_t* zall = nullptr;
     float *xd = nullptr, *od = nullptr;
     const size_t xb_elems = (size_t)batch_size * tile_size * tile_size * 8, z_tile = (size_t)3 * S * S;
+    const int z_f32 = downscale > 1;
+    const size_t zsz = z_f32 ? 4 : 2;
     const size_t oplane = (size_t)cfg.y_h * cfg.y_w;
     NB_CUDA(cudaMallocAsync((void**)&xd, (size_t)C * H * W * 4, st));
     NB_CUDA(cudaMallocAsync((void**)&od, (size_t)C * oplane * 4, st));
-    if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * 2)) return 1;
-    xb = m->frame_xb; zall = m->frame_z;
+    if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * zsz)) return 1;
+    xb = m->frame_xb; zall = reinterpret_cast<uint8_t*>(m->frame_z);
     NB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)C * H * W * 4, cudaMemcpyHostToDevice, st));
     int rc = 0, rows_done = 0;
     for (int t0 = 0; t0 < ntiles && !rc; t0 += batch_size) {
         const int nb = ntiles - t0 < batch_size ? ntiles - t0 : batch_size;
         rc = nb200_tile_unfold(xd, C, H, W, &cfg, tile_size, t0, nb, xb, 8, stream);
-        if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile, stream);
+        if (!rc) rc = nb200_model_forward(m, xb, nb, tile_size, downscale, zall + (size_t)t0 * z_tile * zsz, stream);
         if (rc) break;
         // output rows below the first unfinished tile row are final
         const int rows_full = (t0 + nb) / cfg.w_blocks;
         int y1 = rows_full >= cfg.h_blocks ? cfg.y_h : rows_full * cfg.output_tile_step;
         if (y1 > cfg.y_h) y1 = cfg.y_h;
         if (y1 > rows_done) {
-            rc = tile_gather_blend_rows(zall, C, &cfg, scale, offset, tile_size, blend, od, rows_done, y1, stream);
+            rc = tile_gather_blend_rows(zall, z_f32, C, &cfg, scale, offset, tile_size, blend, od, rows_done, y1, stream);
             if (rc) break;
             cudaEvent_t ev;
             NB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

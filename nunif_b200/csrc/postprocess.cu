@@ -86,6 +86,56 @@ __global__ void __launch_bounds__(128) resize_bicubic_aa_kernel(ResizeParams p) 
     p.out[((size_t)pl * p.oh + oy) * p.ow + ox] = p.clamp ? clamp01(acc) : acc;
 }
 
+
+// ---- VR180: iw3/equirectangular.py:7-40.  Zero-pad to (roughly) a square of 1.5 x the longer edge, then
+// F.grid_sample(bicubic, zeros, align_corners=True) through the mesh  x' = k tan(az), y' = k tan(el) / cos(az).
+// The padded image is never materialised: taps outside the source rectangle contribute 0, exactly like the pad + zeros mode.
+__device__ __forceinline__ float linspace_m1_p1(int idx, int steps) {
+    // torch.linspace(-1, 1, steps) in fp32: start + step*i on the first half, end - step*(steps-1-i) on the second
+    const float step = 2.0f / (float)(steps - 1);
+    return idx < steps / 2 ? -1.0f + step * (float)idx : 1.0f - step * (float)(steps - idx - 1);
+}
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {   // ATen get_cubic_upsample_coefficients, A = -0.75
+    const float A = -0.75f;
+    auto c1 = [&](float x) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; };
+    auto c2 = [&](float x) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; };
+    w[0] = c2(t + 1.f); w[1] = c1(t); w[2] = c1(1.f - t); w[3] = c2(2.f - t);
+}
+__global__ void __launch_bounds__(256) equirect_kernel(const float* __restrict__ c, int C, int H, int W, int pad_h, int pad_w, int Ho, int Wo,
+                                                       float k, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Wo) return;
+    const float x = linspace_m1_p1(j, Wo), y = linspace_m1_p1(i, Ho);
+    const float az = x * 1.5707963267948966f, el = y * 1.5707963267948966f;
+    const float gx = k * tanf(az), gy = k * (tanf(el) / cosf(az));
+    const float ix = ((gx + 1.f) / 2.f) * (float)(Wo - 1), iy = ((gy + 1.f) / 2.f) * (float)(Ho - 1);   // align_corners=True
+    const float fx = floorf(ix), fy = floorf(iy);
+    float wx[4], wy[4];
+    cubic_coeffs(ix - fx, wx);
+    cubic_coeffs(iy - fy, wy);
+    // tap coordinates in the SOURCE image; anything outside is the zero pad / zeros padding mode.  Guard the float->int
+    // conversion: tan() explodes towards the poles.
+    const bool far_away = !(fabsf(fx) < 1e8f && fabsf(fy) < 1e8f);
+    const int x0 = far_away ? -1000000 : (int)fx - 1 - pad_w, y0 = far_away ? -1000000 : (int)fy - 1 - pad_h;
+    for (int ch = 0; ch < C; ++ch) {
+        const float* p = c + (size_t)ch * H * W;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = y0 + a;
+            float row = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = x0 + b;
+                const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(p + (size_t)yy * W + xx) : 0.f;
+                row = row + v * wx[b];
+            }
+            acc = acc + row * wy[a];
+        }
+        out[((size_t)ch * Ho + i) * Wo + j] = clamp01(acc);
+    }
+}
+
 }  // namespace nb200
 
 using namespace nb200;
@@ -114,6 +164,27 @@ extern "C" int nb200_resize_bicubic_aa(const float* x, int planes, int H, int W,
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps(st, PC_OTHER, (double)planes * ((double)H * W + (double)oh * ow) * 4);
     resize_bicubic_aa_kernel<<<dim3(cdiv(ow, 128), oh, planes), 128, 0, st>>>(p);
+    NB_LAUNCHED();
+    return 0;
+}
+
+// iw3/equirectangular.py:7-40 (VR180 output): c [C][H][W] -> out [C][H + 2*pad_h][W + 2*pad_w] (nb200_equirectangular_size)
+extern "C" int nb200_equirectangular_size(int H, int W, int* out_h, int* out_w) {
+    NB_CHECK(out_h && out_w && H > 0 && W > 0, "bad arguments");
+    const int max_edge = H > W ? H : W, output_size = max_edge + max_edge / 2;
+    *out_h = H + 2 * ((output_size - H) / 2);
+    *out_w = W + 2 * ((output_size - W) / 2);
+    return 0;
+}
+extern "C" int nb200_equirectangular(const float* c, int C, int H, int W, float* out, void* stream) {
+    NB_CHECK(c && out, "null pointer");
+    NB_CHECK(C > 0 && H > 0 && W > 0, "bad shape");
+    const int max_edge = H > W ? H : W, output_size = max_edge + max_edge / 2;
+    const int pad_h = (output_size - H) / 2, pad_w = (output_size - W) / 2;
+    const int Ho = H + 2 * pad_h, Wo = W + 2 * pad_w;
+    NB_CHECK(Ho > 1 && Wo > 1, "image too small");
+    const float k = (float)((double)max_edge / (double)output_size);
+    equirect_kernel<<<dim3(cdiv(Wo, 256), Ho), 256, 0, (cudaStream_t)stream>>>(c, C, H, W, pad_h, pad_w, Ho, Wo, k, out);
     NB_LAUNCHED();
     return 0;
 }

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) tile_unfold_kernel(const float* __restric
 }
 
 struct BlendParams {
-    const __half* z;
+    const void* z;        // tile outputs: fp16 (models that return fp16 under autocast) or fp32 (the 4x-derived 2x / 1x models)
     float* out;
     int C, S, y_h, y_w, h_blocks, w_blocks, step_out, blend, y0;
     float ring[65];  // ring[d] = weight at distance d from the tile edge, d < blend
@@ -52,6 +52,22 @@ __device__ __forceinline__ float blend_weight(const BlendParams& p, int u, int v
     return d >= p.blend ? 1.f : p.ring[d];
 }
 
+template <typename ZT> __device__ __forceinline__ float z_at(const void* z, size_t i);
+template <> __device__ __forceinline__ float z_at<__half>(const void* z, size_t i) { return __half2float(reinterpret_cast<const __half*>(z)[i]); }
+template <> __device__ __forceinline__ float z_at<float>(const void* z, size_t i) { return __ldg(reinterpret_cast<const float*>(z) + i); }
+template <typename ZT> __device__ __forceinline__ void z_at4(const void* z, size_t i, float (&v)[4]);
+template <> __device__ __forceinline__ void z_at4<__half>(const void* z, size_t i, float (&v)[4]) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(z) + i));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+}
+template <> __device__ __forceinline__ void z_at4<float>(const void* z, size_t i, float (&v)[4]) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(z) + i));
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+
+template <typename ZT>
 __global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
     const int X = blockIdx.x * blockDim.x + threadIdx.x;
     const int Y = blockIdx.y + p.y0;
@@ -71,7 +87,7 @@ __global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
             for (int b = 0; b < nw; ++b) {
                 const int u = Y - his[a] * p.step_out, v = X - wis[b] * p.step_out;
                 const size_t t = (size_t)his[a] * p.w_blocks + wis[b];
-                const float zv = __half2float(p.z[(t * p.C + c) * zplane + (size_t)u * p.S + v]);
+                const float zv = z_at<ZT>(p.z, (t * p.C + c) * zplane + (size_t)u * p.S + v);
                 if (p.blend > 0) {
                     const float w = blend_weight(p, u, v);
                     num += w * zv;
@@ -87,6 +103,7 @@ __global__ void __launch_bounds__(256) tile_gather_blend_kernel(BlendParams p) {
 
 // 4 horizontally adjacent output pixels per thread (valid when y_w, the tile step and S are multiples of 4, so a
 // group never straddles a tile edge): 8-byte fp16 loads, one float4 store per colour plane.
+template <typename ZT>
 __global__ void __launch_bounds__(256) tile_gather_blend4_kernel(BlendParams p) {
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int Y = blockIdx.y + p.y0;
@@ -105,10 +122,8 @@ __global__ void __launch_bounds__(256) tile_gather_blend4_kernel(BlendParams p) 
             for (int b = 0; b < nw; ++b) {
                 const int u = Y - his[a] * p.step_out, v = X - wis[b] * p.step_out;
                 const size_t t = (size_t)his[a] * p.w_blocks + wis[b];
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.z + (t * p.C + c) * zplane + (size_t)u * p.S + v));
-                const __half2* h = reinterpret_cast<const __half2*>(&raw);
-                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                const float zv[4] = {f0.x, f0.y, f1.x, f1.y};
+                float zv[4];
+                z_at4<ZT>(p.z, (t * p.C + c) * zplane + (size_t)u * p.S + v, zv);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (p.blend > 0) {
@@ -172,17 +187,17 @@ extern "C" int nb200_tile_unfold(const float* x, int C, int H, int W, const nb20
 extern "C" int nb200_tile_gather_blend(const void* z_all, int C, const nb200_tile_config* cfg, int scale, int offset,
                                        int tile_size, int blend_size, float* out, void* stream) {
     NB_CHECK(cfg, "null pointer");
-    return nb200::tile_gather_blend_rows(z_all, C, cfg, scale, offset, tile_size, blend_size, out, 0, cfg->y_h, stream);
+    return nb200::tile_gather_blend_rows(z_all, 0, C, cfg, scale, offset, tile_size, blend_size, out, 0, cfg->y_h, stream);
 }
 
 // rows [y0, y1) of the blended output; every tile covering those rows must already be in z_all
-int nb200::tile_gather_blend_rows(const void* z_all, int C, const nb200_tile_config* cfg, int scale, int offset, int tile_size,
+int nb200::tile_gather_blend_rows(const void* z_all, int z_f32, int C, const nb200_tile_config* cfg, int scale, int offset, int tile_size,
                                   int blend_size, float* out, int y0, int y1, void* stream) {
     NB_CHECK(z_all && cfg && out, "null pointer");
     NB_CHECK(0 <= y0 && y0 < y1 && y1 <= cfg->y_h, "bad row range");
     NB_CHECK(blend_size >= 0 && blend_size <= 64, "blend_size out of range");
     BlendParams p;
-    p.z = (const __half*)z_all;
+    p.z = z_all;
     p.out = out;
     p.C = C;
     p.S = tile_size * scale - 2 * offset;
@@ -199,10 +214,16 @@ int nb200::tile_gather_blend_rows(const void* z_all, int C, const nb200_tile_con
     const double frac = (double)(y1 - y0) / p.y_h;
     ProfScope ps((cudaStream_t)stream, PC_BLEND,
                  frac * ((double)C * p.y_h * p.y_w * 4 + (double)p.h_blocks * p.w_blocks * C * p.S * p.S * 2));
-    if (p.y_w % 4 == 0 && p.step_out % 4 == 0 && p.S % 4 == 0 && ((uintptr_t)out & 15) == 0)
-        tile_gather_blend4_kernel<<<dim3(cdiv(p.y_w / 4, 256), y1 - y0), 256, 0, (cudaStream_t)stream>>>(p);
-    else
-        tile_gather_blend_kernel<<<dim3(cdiv(p.y_w, 256), y1 - y0), 256, 0, (cudaStream_t)stream>>>(p);
+    const bool vec4 = p.y_w % 4 == 0 && p.step_out % 4 == 0 && p.S % 4 == 0 && ((uintptr_t)out & 15) == 0;
+    const dim3 g4(cdiv(p.y_w / 4, 256), y1 - y0), g1(cdiv(p.y_w, 256), y1 - y0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (z_f32) {
+        if (vec4) tile_gather_blend4_kernel<float><<<g4, 256, 0, st>>>(p);
+        else tile_gather_blend_kernel<float><<<g1, 256, 0, st>>>(p);
+    } else {
+        if (vec4) tile_gather_blend4_kernel<__half><<<g4, 256, 0, st>>>(p);
+        else tile_gather_blend_kernel<__half><<<g1, 256, 0, st>>>(p);
+    }
     NB_LAUNCHED();
     return 0;
 }

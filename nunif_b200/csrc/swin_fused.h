@@ -16,8 +16,14 @@ struct FusedMlp {
     const float* b1 = nullptr;
     const __half* w2 = nullptr;   // [C][2C]
     const float* b2 = nullptr;
+    // chunk-major copies [K/BK][rows][BK] (BK = 64 for C = 192, 32 for C = 96) for the half-SM kernel (swin_fused_mlp2.cu)
+    const __half* w1_cm = nullptr;
+    const __half* wp_cm = nullptr;
 };
 int swin_mlp_fused(cudaStream_t st, const FusedMlp& f);
+// two CTAs per SM; C = 96: proj fused (att, wp_cm, bp), C = 192: MLP only (att must be null; the proj Linear runs as a GEMM)
+int swin_mlp_fused2(cudaStream_t st, const FusedMlp& f);
+int pack_chunk_major(cudaStream_t st, const __half* w, __half* out, int rows, int K, int bk);
 
 // att <- window_attention(x.Wqkv^T + bqkv)  (everything of shifted_window_attention but the proj Linear).
 // x, att: [B][H][W][C] fp16; wqkv_packed: rows regrouped per head pair (pack_qkv_for_fused); bias_tab: [6][36][40] fp32

@@ -7,21 +7,27 @@
 // writes att (2*C*2 bytes per token).
 //
 // One persistent CTA per SM walks tiles of 3 windows (108 tokens, padded to the 128 rows of one UMMA):
-//   warp 0       TMA producer: the window gather is done by the TMA unit - one (64 ch, 6, 6) box per window and K-chunk
-//                lands the window's 36 tokens as 36 consecutive 128B-swizzled rows (windows that wrap around the rolled
-//                image use 3-wide single-row boxes); weight K-chunks of the current head pair stream through a ring
-//   warp 1       tcgen05.mma issuer: D[pair] (128 x 6d) = X (128 x C) . Wqkv[pair]^T, two TMEM accumulators (ping-pong)
-//   warps 2-9    GEMM epilogue: TMEM -> + bias -> fp16 -> q | k | v of the head pair as padded row-major matrices in
-//                shared memory (double buffered)
-//   warps 10-18  attention: warp = (window, 16-row query tile); S = QK^T and O = PV on mma.sync.m16n8k16 with the
-//                probabilities kept in registers (a 36x36xd problem per head is far below a tcgen05 tile), base-2 softmax,
-//                bias table in shared memory, output rows staged over the dead q rows and stored as full 128-byte lines
-//                (2 heads x 32 channels) at their un-rolled token positions.
+//   warpgroup 0 (24 regs/thread): warps 0 / 2 weight producers (even / odd ring slots), warp 1 tcgen05.mma issuer
+//                (D[pair] (128 x 6d) = X (128 x C) . Wqkv[pair]^T, two TMEM accumulators, ping-pong), warp 3 activation
+//                producer.  The window gather is done by the TMA unit - one (64 ch, 6, 6) box per window and K-chunk lands
+//                the window's 36 tokens as 36 consecutive 128B-swizzled rows (windows that wrap around the rolled image use
+//                3-wide single-row boxes).  Bulk-tensor ops of one warp execute one after the other (~0.34 us each,
+//                profiles/r2/tma_inflight.json), hence one warp per stream.
+//   warpgroups 1-2 (48 regs): 8 GEMM-epilogue warps: TMEM -> + bias -> fp16 -> q | k | v of the head pair as padded row-major
+//                matrices in shared memory (double buffered)
+//   warpgroups 3-6 (96 regs): 16 attention warps, one task each per head pair: (window, head, 16-row query tile); S = QK^T and
+//                O = PV on mma.sync.m16n8k16 with the probabilities kept in registers (a 36x36xd problem per head is far
+//                below a tcgen05 tile), base-2 softmax, bias table in shared memory, output rows staged over the dead q rows
+//                and stored at their un-rolled token positions.  A clock64 timeline of the first version (9 attention warps,
+//                profiles/r2/fused_timeline_attn_192.txt) showed these latency-bound warps as THE bottleneck; registers
+//                for 16 of them come from setmaxnreg (the CTA launches at 72 registers x 896 threads).
 #include "gemm_tcgen05.cuh"
 #include "swin_fused.h"
 #include "tmap.h"
 
 namespace nb200 {
+
+extern unsigned long long* g_timeline;   // gemm.cu (nb200_debug_timeline)
 
 namespace {
 
@@ -71,12 +77,16 @@ struct FaCfg {
     static constexpr int XCH = 128 * 128;                   // bytes of one [128][64] chunk
     static constexpr int XB = KCH * XCH;
     static constexpr int WST = NCHK * 128;                  // weight ring stage: [6d][64] fp16
-    static constexpr int STAGES = (C == 192) ? 2 : 6;
+    static constexpr int STAGES = (C == 192) ? 2 : 6;       // even: slot s is owned by producer s & 1
+    static_assert(STAGES % 2 == 0, "ring slots are split between two producers");
     static constexpr int QKV_MAT = WPT * WTOK * LDH * 2;    // one matrix (q, k or v) of a head pair, all 3 windows
     static constexpr int QKV_BUF = 3 * QKV_MAT;
     static constexpr int TMEM_COLS = 2 * NCHK <= 256 ? 256 : 512;
-    static constexpr int EPI_WARPS = 8, ATT_WARPS = 9;
-    static constexpr int THREADS = 64 + 32 * (EPI_WARPS + ATT_WARPS);
+    static constexpr int EPI_WARPS = 8, ATT_WARPS = 16;    // + warpgroup 0: 2 weight producers, MMA, activation producer
+    static constexpr int THREADS = 32 * (4 + EPI_WARPS + ATT_WARPS);   // 896 = 7 warpgroups, launched at 72 registers/thread
+    // setmaxnreg re-distributes the CTA's LAUNCH-TIME pool (72 registers x 896 threads = 64512), not the whole register file
+    static constexpr int REG_LAUNCH = 72, REG_CTRL = 24, REG_EPI = 48, REG_ATT = 96;    // 128*24 + 256*48 + 512*96 = 64512
+    static_assert(128 * REG_CTRL + 256 * REG_EPI + 512 * REG_ATT <= REG_LAUNCH * THREADS, "register pool of the CTA");
     static constexpr size_t SMEM = 1024 + (size_t)XB + 2 * QKV_BUF + BT_FLOATS * 4 + (size_t)STAGES * WST + 3 * C * 4 + 256;
 };
 
@@ -86,6 +96,7 @@ struct FusedAttnMaps {
     CUtensorMap w;     // packed Wqkv [3C][C], box (64, 6d)
 };
 struct FusedAttnParams {
+    unsigned long long* tl;   // optional debug timeline (nb200_debug_timeline)
     int B, H, W, shift;
     int nww, nwh, nwin, tiles;
     const float* bqkv;       // packed order
@@ -213,6 +224,12 @@ __device__ __forceinline__ void fa_mtile(const __half* sq, const __half* sk, con
     }
 }
 
+// Register re-allocation between warpgroups (sm_90+): the CTA starts with 72 registers per thread (896 threads); the producer /
+// MMA warpgroup and the two epilogue warpgroups give registers back, the four attention warpgroups take them (24 / 48 / 96).
+// The pool is what the CTA was launched with (72 x 896 = 64512), so the three figures must add up to no more than that.
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <int C>
 __global__ void __launch_bounds__(FaCfg<C>::THREADS, 1) swin_attn_fused_kernel(const __grid_constant__ FusedAttnMaps maps,
                                                                                const __grid_constant__ FusedAttnParams p) {
@@ -233,12 +250,16 @@ __global__ void __launch_bounds__(FaCfg<C>::THREADS, 1) swin_attn_fused_kernel(c
     uint64_t* x_full = w_empty + S;
     uint64_t* x_empty = x_full + 1;
     uint64_t* d_full = x_empty + 1;     // [2]
-    uint64_t* d_empty = d_full + 2;     // [2]  8 epilogue warps
-    uint64_t* qkv_full = d_empty + 2;   // [2]  8 epilogue warps
-    uint64_t* qkv_empty = qkv_full + 2; // [2]  9 attention warps
+    uint64_t* d_empty = d_full + 2;     // [2]  epilogue warps
+    uint64_t* qkv_full = d_empty + 2;   // [2]  epilogue warps
+    uint64_t* qkv_empty = qkv_full + 2; // [2]  attention warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qkv_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // debug timeline: tracks 0 weights producer, 1 activation producer, 2 MMA, 3 first epilogue warp, 4/5 attention warps 0/12
+    unsigned long long* tlb = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
+    int tli = 0;
+#define FTL(track, tag, aux) do { if (tlb && tli < 2048) { tlb[(track) * 2048 + tli] = ((unsigned long long)(tag) << 56) | ((unsigned long long)((aux) & 0xffff) << 40) | (clock64() & 0xffffffffffull); ++tli; } } while (0)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.xw);
@@ -266,95 +287,120 @@ __global__ void __launch_bounds__(FaCfg<C>::THREADS, 1) swin_attn_fused_kernel(c
     const int first = blockIdx.x, stride = gridDim.x;
     const int wpi = p.nww * p.nwh;   // windows per image
 
-    if (warp == 0) {
-        // ===================== TMA producer (one thread) =====================
-        if (elect_one() && first < p.tiles) {
-            int ws = 0;
-            uint32_t wph = 0, par = 0;
-            bool waited = false;
-            for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
-                if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
-                // ---- activation tile: 3 windows gathered by the TMA unit
-                mbar_wait(x_empty, par ^ 1);
-                int nvalid = p.nwin - tile * WPT;
-                if (nvalid > WPT) nvalid = WPT;
-                mbar_expect_tx(x_full, (uint32_t)(nvalid * WTOK * 128 * KCH));
-                for (int wi = 0; wi < nvalid; ++wi) {
-                    const int win = tile * WPT + wi;
-                    const int b = win / wpi, rem = win - b * wpi;
-                    const int wy = rem / p.nww, wx = rem - wy * p.nww;
-                    const int y0 = wy * WS + p.shift, x0 = wx * WS + p.shift;   // torch.roll(-shift): window row r <- row (r + shift) % H
-                    uint8_t* dst = sX + wi * WTOK * 128;
-                    if (y0 + WS <= p.H && x0 + WS <= p.W) {
-                        for (int kc = 0; kc < KCH; ++kc) tma_load_4d(&maps.xw, x_full, dst + kc * XCH, kc * 64, x0, y0, b);
-                    } else {
-                        for (int yy = 0; yy < WS; ++yy) {
-                            int y = y0 + yy; if (y >= p.H) y -= p.H;
-                            for (int hx = 0; hx < 2; ++hx) {
-                                int x = x0 + 3 * hx; if (x >= p.W) x -= p.W;
-                                for (int kc = 0; kc < KCH; ++kc)
-                                    tma_load_4d(&maps.xh, x_full, dst + kc * XCH + (yy * WS + 3 * hx) * 128, kc * 64, x, y, b);
+    if (warp < 4) {
+        // ============ warpgroup 0: warp 0 / 2 weight producers (even / odd ring slots), warp 1 MMA, warp 3 activation producer
+        reg_dec<Cfg::REG_CTRL>();
+        if (warp == 3) {
+            // ---- activation tile: 3 windows gathered by the TMA unit (bulk ops of one warp run one after the other, ~0.34 us each:
+            //      profiles/r2/tma_inflight.json - 9 ops per tile stay well under the tile time, the weights have their own warps)
+            if (elect_one() && first < p.tiles) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                uint32_t par = 0;
+                for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
+                    FTL(1, 1, 0);
+                    mbar_wait(x_empty, par ^ 1);
+                    FTL(1, 2, 0);
+                    int nvalid = p.nwin - tile * WPT;
+                    if (nvalid > WPT) nvalid = WPT;
+                    mbar_expect_tx(x_full, (uint32_t)(nvalid * WTOK * 128 * KCH));
+                    for (int wi = 0; wi < nvalid; ++wi) {
+                        const int win = tile * WPT + wi;
+                        const int b = win / wpi, rem = win - b * wpi;
+                        const int wy = rem / p.nww, wx = rem - wy * p.nww;
+                        const int y0 = wy * WS + p.shift, x0 = wx * WS + p.shift;   // torch.roll(-shift): window row r <- row (r + shift) % H
+                        uint8_t* dst = sX + wi * WTOK * 128;
+                        if (y0 + WS <= p.H && x0 + WS <= p.W) {
+                            for (int kc = 0; kc < KCH; ++kc) tma_load_4d(&maps.xw, x_full, dst + kc * XCH, kc * 64, x0, y0, b);
+                        } else {
+                            for (int yy = 0; yy < WS; ++yy) {
+                                int y = y0 + yy; if (y >= p.H) y -= p.H;
+                                for (int hx = 0; hx < 2; ++hx) {
+                                    int x = x0 + 3 * hx; if (x >= p.W) x -= p.W;
+                                    for (int kc = 0; kc < KCH; ++kc)
+                                        tma_load_4d(&maps.xh, x_full, dst + kc * XCH + (yy * WS + 3 * hx) * 128, kc * 64, x, y, b);
+                                }
                             }
                         }
                     }
                 }
-                // ---- weights of the 3 head pairs
-                for (int c = 0; c < Cfg::NPAIR; ++c)
+            }
+        } else if (warp != 1) {
+            // ---- weights of the 3 head pairs, K-chunk by K-chunk; ring slot ws belongs to producer ws & 1 (fixed ownership:
+            //      mbarrier waits are 1-bit phase parities, a thread must see every phase of a barrier it waits on)
+            const int pid = warp >> 1;
+            if (elect_one() && first < p.tiles) {
+                int ws = 0;
+                uint32_t wph = 0;
+                for (int tile = first; tile < p.tiles; tile += stride)
+                    for (int c = 0; c < Cfg::NPAIR; ++c)
+                        for (int kc = 0; kc < KCH; ++kc) {
+                            if ((ws & 1) == pid) {
+                                if (pid == 0) FTL(0, 3, c);
+                                mbar_wait(&w_empty[ws], wph ^ 1);
+                                if (pid == 0) FTL(0, 4, c);
+                                mbar_expect_tx(&w_full[ws], WST);
+                                tma_load_2d(&maps.w, &w_full[ws], sW + ws * WST, kc * 64, c * NCHK);
+                            }
+                            if (++ws == S) { ws = 0; wph ^= 1; }
+                        }
+            }
+        } else {
+            // ---- MMA issuer
+            const uint32_t idesc = make_idesc_f16(NCHK);
+            const uint32_t aX = smem_u32(sX), aW = smem_u32(sW);
+            int ws = 0;
+            uint32_t wph = 0, par = 0, gc = 0;
+            for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
+                if (lane == 0) FTL(2, 10, 0);
+                mbar_wait(x_full, par);
+                tc_fence_after();
+                if (lane == 0) FTL(2, 11, 0);
+                for (int c = 0; c < Cfg::NPAIR; ++c, ++gc) {
+                    const uint32_t buf = gc & 1, ph = (gc >> 1) & 1;
+                    mbar_wait(&d_empty[buf], ph ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) FTL(2, 12, c);
+                    const uint32_t td = tmem_base + buf * NCHK;
                     for (int kc = 0; kc < KCH; ++kc) {
-                        mbar_wait(&w_empty[ws], wph ^ 1);
-                        mbar_expect_tx(&w_full[ws], WST);
-                        tma_load_2d(&maps.w, &w_full[ws], sW + ws * WST, kc * 64, c * NCHK);
+                        mbar_wait(&w_full[ws], wph);
+                        tc_fence_after();
+                        if (lane == 0) FTL(2, 13, kc);
+                        if (elect_one()) {
+                            const int ksteps = kc == KCH - 1 ? Cfg::KLAST : 4;
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_f16(td, make_kmajor_desc<128>(aX + kc * XCH + k * 32), make_kmajor_desc<128>(aW + ws * WST + k * 32),
+                                         idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(&w_empty[ws]);
+                            if (kc == KCH - 1) {
+                                umma_commit(&d_full[buf]);
+                                if (c == Cfg::NPAIR - 1) umma_commit(x_empty);   // the activation tile may be overwritten
+                            }
+                        }
+                        __syncwarp();
                         if (++ws == S) { ws = 0; wph ^= 1; }
                     }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = make_idesc_f16(NCHK);
-        const uint32_t aX = smem_u32(sX), aW = smem_u32(sW);
-        int ws = 0;
-        uint32_t wph = 0, par = 0, gc = 0;
-        for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
-            mbar_wait(x_full, par);
-            tc_fence_after();
-            for (int c = 0; c < Cfg::NPAIR; ++c, ++gc) {
-                const uint32_t buf = gc & 1, ph = (gc >> 1) & 1;
-                mbar_wait(&d_empty[buf], ph ^ 1);
-                tc_fence_after();
-                const uint32_t td = tmem_base + buf * NCHK;
-                for (int kc = 0; kc < KCH; ++kc) {
-                    mbar_wait(&w_full[ws], wph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const int ksteps = kc == KCH - 1 ? Cfg::KLAST : 4;
-                        for (int k = 0; k < ksteps; ++k)
-                            umma_f16(td, make_kmajor_desc<128>(aX + kc * XCH + k * 32), make_kmajor_desc<128>(aW + ws * WST + k * 32),
-                                     idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                        umma_commit(&w_empty[ws]);
-                        if (kc == KCH - 1) {
-                            umma_commit(&d_full[buf]);
-                            if (c == Cfg::NPAIR - 1) umma_commit(x_empty);   // the activation tile may be overwritten
-                        }
-                    }
-                    __syncwarp();
-                    if (++ws == S) { ws = 0; wph ^= 1; }
                 }
             }
         }
-    } else if (warp < 2 + Cfg::EPI_WARPS) {
-        // ===================== GEMM epilogue (warps 2..9): TMEM -> q | k | v in shared memory =====================
-        const int g = warp & 3, hq = (warp - 2) >> 2;   // TMEM lane group, column half
+    } else if (warp < 4 + Cfg::EPI_WARPS) {
+        // ============ warpgroups 1-2: GEMM epilogue (warps 4..11): TMEM -> + bias -> fp16 -> q | k | v in shared memory
+        reg_dec<Cfg::REG_EPI>();
+        const int g = warp & 3, hq = (warp - 4) >> 2;   // TMEM lane group, column half
         const int r = g * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(g * 32) << 16);
         constexpr int NPW = NCHK / 16;                  // 8-column pieces per warp: 12 (C=192) or 6 (C=96)
-        constexpr int GP = (NPW % 4 == 0) ? 4 : 3;      // pieces per TMEM wait
+        constexpr int GP = 2;                           // pieces per TMEM wait (48 registers per thread here)
         uint32_t gc = 0;
         for (int tile = first; tile < p.tiles; tile += stride) {
             for (int c = 0; c < Cfg::NPAIR; ++c, ++gc) {
                 const uint32_t buf = gc & 1, ph = (gc >> 1) & 1;
+                const bool tle = warp == 4 && lane == 0;
+                if (tle) FTL(3, 20, c);
                 mbar_wait(&d_full[buf], ph);
                 tc_fence_after();
+                if (tle) FTL(3, 21, c);
                 mbar_wait(&qkv_empty[buf], ph ^ 1);
+                if (tle) FTL(3, 22, c);
                 uint8_t* qb = sQKV + buf * Cfg::QKV_BUF;
                 const float* bia = sBias + c * NCHK;
 #pragma unroll 1
@@ -381,18 +427,25 @@ __global__ void __launch_bounds__(FaCfg<C>::THREADS, 1) swin_attn_fused_kernel(c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&d_empty[buf]); mbar_arrive(&qkv_full[buf]); }
+                if (tle) FTL(3, 23, c);
             }
         }
     } else {
-        // ===================== attention warps (9): warp = (window in tile, query m-tile) =====================
-        const int a = warp - (2 + Cfg::EPI_WARPS);
-        const int wi = a / 3, mt = a - wi * 3;
+        // ============ warpgroups 3-6: 16 attention warps.  Per head pair: 12 full tasks (window, head, 16-row query tile 0/1) on
+        // warps 0..11, the 6 quarter-size last query tiles (rows 32..35, both heads of a window) on warps 12..14; warp 15 idles.
+        reg_inc<Cfg::REG_ATT>();
+        const int a = warp - (4 + Cfg::EPI_WARPS);
+        const bool last_task = a >= 12;
+        const int wi = last_task ? a - 12 : a >> 2;
+        const int mt = last_task ? 2 : (a & 1);
+        const int hh0 = last_task ? 0 : ((a >> 1) & 1), nh = last_task ? 2 : 1;   // heads of the pair handled by this warp
+        const bool idle = a == 15;
         const float scale = ((D == 16) ? 0.25f : 0.17677669529663687f) * 1.4426950408889634f;   // d^-0.5 (:187) * log2(e)
-        constexpr int PPR = (2 * D * 2) / 16;           // 16-byte pieces per output row of a head pair: 8 or 4
+        constexpr int PPH = (D * 2) / 16;               // 16-byte pieces per output row of ONE head: 4 or 2
         uint32_t gc = 0;
         for (int tile = first; tile < p.tiles; tile += stride) {
             const int win = tile * WPT + wi;
-            const bool valid = win < p.nwin;
+            const bool valid = !idle && win < p.nwin;
             int b = 0, wy = 0, wx = 0;
             if (valid) { b = win / wpi; const int rem = win - b * wpi; wy = rem / p.nww; wx = rem - wy * p.nww; }
             const bool boundary = p.shift > 0 && (wy == p.nwh - 1 || wx == p.nww - 1);   // only these windows mix mask regions
@@ -410,22 +463,31 @@ __global__ void __launch_bounds__(FaCfg<C>::THREADS, 1) swin_attn_fused_kernel(c
             }
             for (int c = 0; c < Cfg::NPAIR; ++c, ++gc) {
                 const uint32_t buf = gc & 1, ph = (gc >> 1) & 1;
+                const bool tla = (a == 0 || a == 12) && lane == 0;
+                const int ttr = a == 0 ? 4 : 5;
+                if (tla) FTL(ttr, 30, c);
                 mbar_wait(&qkv_full[buf], ph);
+                if (tla) FTL(ttr, 31, c);
                 if (valid) {
                     __half* mq = reinterpret_cast<__half*>(sQKV + buf * Cfg::QKV_BUF) + wi * WTOK * LDH;
                     const __half* mk = mq + Cfg::QKV_MAT / 2;
                     const __half* mv = mk + Cfg::QKV_MAT / 2;
 #pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
+                    for (int hi = 0; hi < nh; ++hi) {
+                        const int hh = hh0 + hi;
                         const float* bt = sBT + (c * 2 + hh) * WTOK * BT_LD;
                         if (mt < 2) fa_mtile<D, LDH, false>(mq, mk, mv, bt, mt, hh * D, lane, scale, boundary, reg_lo, reg_hi);
                         else fa_mtile<D, LDH, true>(mq, mk, mv, bt, mt, hh * D, lane, scale, boundary, reg_lo, reg_hi);
                     }
                     __syncwarp();
-                    // rows [16 mt, 16 mt + 16) x the pair's 2d channels -> att at the un-rolled token positions
+                    if (tla) FTL(ttr, 32, c);
+                    // rows [16 mt, 16 mt + 16) x this warp's head columns -> att at the un-rolled token positions
+                    // (staging the rows in registers and releasing the buffer before the global stores was measured SLOWER:
+                    //  626 -> 760 us on the 921 600-token launch, the extra live registers spill in all 16 warps)
                     const int nrows = mt < 2 ? 16 : WTOK - 32;
-                    for (int idx = lane; idx < nrows * PPR; idx += 32) {
-                        const int i = mt * 16 + idx / PPR, pc = idx % PPR;
+                    const int ppr = PPH * nh;                                     // pieces per row written by this warp
+                    for (int idx = lane; idx < nrows * ppr; idx += 32) {
+                        const int i = mt * 16 + idx / ppr, pc = hh0 * PPH + idx % ppr;
                         int y = wy * WS + i / WS + p.shift, x = wx * WS + i % WS + p.shift;
                         if (y >= p.H) y -= p.H;
                         if (x >= p.W) x -= p.W;
@@ -435,6 +497,7 @@ __global__ void __launch_bounds__(FaCfg<C>::THREADS, 1) swin_attn_fused_kernel(c
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&qkv_empty[buf]);
+                if (tla) FTL(ttr, 33, c);
             }
         }
     }
@@ -469,6 +532,7 @@ static int launch_attn(cudaStream_t st, const FusedAttn& f) {
     p.nwin = f.B * p.nww * p.nwh;
     p.tiles = (p.nwin + WPT - 1) / WPT;
     p.bqkv = f.bqkv; p.bias_tab = f.bias_tab; p.att = f.att;
+    p.tl = g_timeline;
     if (ensure_dyn_smem((const void*)swin_attn_fused_kernel<C>, Cfg::SMEM)) return 1;
     int grid = device_sm_count();
     if (grid > p.tiles) grid = p.tiles;

@@ -7,7 +7,11 @@
 // x1 and the 2C-wide hidden activation live in shared memory / TMEM (round 1 wrote and re-read x1, and the hidden
 // tensor twice: 18*C*2 bytes per token and block -> 5*C*2 with the attention kernel of swin_fused_attn.cu).
 //
-//   warp 0      TMA producer: att tile, x tile, and the weight K-chunks of all three GEMMs through one ring
+//   warps 0,18,19  THREE TMA producer warps.  Measured on this part (profiles/r2/tma_inflight.json): bulk-tensor loads issued
+//               by ONE warp are executed strictly one after the other at ~0.34 us per op whatever their size (4 KB .. 72 KB),
+//               while ops from different warps overlap perfectly.  So every load op of the CTA's sequence - the K-chunks
+//               of the att / x tiles and the weight K-chunks of the three GEMMs (one ring) - is dealt round-robin to the
+//               three producer warps, and the three output chunk stores go out from three different epilogue warps
 //   warp 1      tcgen05.mma issuer (single thread):
 //                 G0  D0[128 x C]      = att  . Wp^T                 (PROJ)
 //                 G1  D1[j][128 x HCH] = x1   . W1[j]^T              hidden chunk j (two accumulators, ping-pong)
@@ -24,6 +28,9 @@
 #include "tmap.h"
 
 namespace nb200 {
+
+extern unsigned long long* g_timeline;   // gemm.cu (nb200_debug_timeline)
+extern int g_tune[16];                    // gemm.cu (nb200_tune_set)
 
 namespace {
 
@@ -56,6 +63,7 @@ struct FmCfg {
     static_assert(2 * HCH + C <= 512, "TMEM budget");
     static_assert(C <= 2 * HCH, "D0 must fit in the D1 columns");
     static_assert(HID % HCH == 0 && HCH % BK == 0 && C % BK == 0, "chunking");
+    static_assert(KCH == 3, "one activation K-chunk per producer warp");
     static constexpr int NBIAS = 4 * C;                     // bp | b1 (2C) | b2
     static constexpr size_t smem_bytes(bool proj) {
         return 1024 + (size_t)XB * (proj ? 2 : 1) + (size_t)NHB * XCH + (size_t)STAGES * WST + NBIAS * 4 + 512;
@@ -68,9 +76,11 @@ struct FusedMlpMaps {
 struct FusedMlpParams {
     int tiles;
     const float *bp, *b1, *b2;
+    unsigned long long* tl;   // optional debug timeline (nb200_debug_timeline): CTA 0 records (tag << 56 | aux << 40 | clock)
 };
 
-constexpr int FM_THREADS = 64 + 32 * 16;
+constexpr int FM_PRODUCERS = 3;                          // warp 0 and warps 18, 19 (640 threads keep 96 registers per thread)
+constexpr int FM_THREADS = 64 + 32 * 16 + 32 * (FM_PRODUCERS - 1);
 
 // one accumulator [128 x C] + bias + residual(in smem) -> fp16 written in place over the residual tile
 template <int C>
@@ -132,6 +142,10 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // debug timeline: 8 role tracks of 2048 events (producers 0-2, MMA, epilogue warp 2)
+    unsigned long long* tlb = (p.tl && blockIdx.x == 0) ? p.tl : nullptr;
+    int tli = 0;
+#define FTL(track, tag, aux) do { if (tlb && tli < 2048) { tlb[(track) * 2048 + tli] = ((unsigned long long)(tag) << 56) | ((unsigned long long)((aux) & 0xffff) << 40) | (clock64() & 0xffffffffffull); ++tli; } } while (0)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.x);
@@ -141,8 +155,8 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
         for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < NHB; ++s) { mbar_init(&h_full[s], 16); mbar_init(&h_empty[s], 1); }
         mbar_init(&d1_full[0], 1); mbar_init(&d1_full[1], 1);
-        mbar_init(att_full, 1); mbar_init(att_empty, 1);
-        mbar_init(x_full, 1); mbar_init(x_empty, 1);
+        mbar_init(att_full, KCH); mbar_init(att_empty, 1);
+        mbar_init(x_full, KCH); mbar_init(x_empty, KCH);
         mbar_init(d0_full, 1); mbar_init(x1_ready, 16); mbar_init(d2_full, 1);
         fence_barrier_init();
     }
@@ -161,16 +175,33 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
     const uint32_t tmem_base = *tmem_slot;
     const int first = blockIdx.x, stride = gridDim.x;
 
-    if (warp == 0) {
-        // ===================== TMA producer (one thread) =====================
+    if (warp == 0 || warp >= 18) {
+        // ===================== TMA producers (one thread in each of 3 warps) =====================
+        // Fixed ownership (mbarrier waits are 1-bit phase parities: a thread must see EVERY phase of a barrier it waits on, so a
+        // ring slot is always refilled by the same producer): weight ring slot s belongs to producer s % 3, K-chunk kc of the
+        // att / x tiles to producer kc (KCH == 3).  Every producer walks the whole op sequence to keep slots and phases.
+        const int pid = warp == 0 ? 0 : warp - 17;
         if (elect_one() && first < p.tiles) {
-            int ws = 0;
+            int ws = 0, wown = 0;            // ring slot and its owner (ws % FM_PRODUCERS, kept incrementally)
             uint32_t wph = 0;
             auto load_w = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
-                mbar_wait(&w_empty[ws], wph ^ 1);
-                mbar_expect_tx(&w_full[ws], bytes);
-                tma_load_2d(m, &w_full[ws], sW + ws * WST, c0, c1);
-                if (++ws == S) { ws = 0; wph ^= 1; }
+                if (wown == pid) {
+                    FTL(pid, 1, ws);
+                    mbar_wait(&w_empty[ws], wph ^ 1);
+                    FTL(pid, 2, ws);
+                    mbar_expect_tx(&w_full[ws], bytes);
+                    tma_load_2d(m, &w_full[ws], sW + ws * WST, c0, c1);
+                }
+                if (++wown == FM_PRODUCERS) wown = 0;
+                if (++ws == S) { ws = 0; wown = 0; wph ^= 1; }
+            };
+            auto load_act = [&](const CUtensorMap* m, uint64_t* full, uint64_t* empty, uint8_t* dst, int row0, uint32_t par) {
+                const int kc = pid;          // static_assert(KCH == FM_PRODUCERS)
+                FTL(pid, 3, empty == x_empty ? 1 : 0);
+                mbar_wait(empty, par ^ 1);
+                FTL(pid, 4, empty == x_empty ? 1 : 0);
+                mbar_expect_tx(full, XCH);
+                tma_load_2d(m, full, dst + kc * XCH, kc * BK, row0);
             };
             auto g1w = [&](int j) {
                 for (int kc = 0; kc < KCH; ++kc) load_w(&maps.w1, kc * BK, j * HCH, HCH * BK * 2);
@@ -182,28 +213,15 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
             uint32_t par = 0;
             for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
                 const int row0 = tile * 128;
+                // weights are launch constants: the first tile's proj chunks go out before the grid dependency resolves
+                if (PROJ && !waited) for (int kc = 0; kc < KCH; ++kc) load_w(&maps.wp, kc * BK, 0, C * BK * 2);
+                if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
                 if (PROJ) {
-                    // weights are launch constants: the first tile's proj chunks go out before the grid dependency resolves
-                    if (!waited) {
-                        for (int kc = 0; kc < KCH; ++kc) load_w(&maps.wp, kc * BK, 0, C * BK * 2);
-                        asm volatile("griddepcontrol.wait;" ::: "memory");
-                        waited = true;
-                        mbar_wait(att_empty, par ^ 1);
-                        mbar_expect_tx(att_full, XB);
-                        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(&maps.att, att_full, sATT + kc * XCH, kc * BK, row0);
-                    } else {
-                        mbar_wait(att_empty, par ^ 1);
-                        mbar_expect_tx(att_full, XB);
-                        for (int kc = 0; kc < KCH; ++kc) tma_load_2d(&maps.att, att_full, sATT + kc * XCH, kc * BK, row0);
-                        for (int kc = 0; kc < KCH; ++kc) load_w(&maps.wp, kc * BK, 0, C * BK * 2);
-                    }
-                } else if (!waited) {
-                    asm volatile("griddepcontrol.wait;" ::: "memory");
-                    waited = true;
+                    load_act(&maps.att, att_full, att_empty, sATT, row0, par);
+                    if (waited) for (int kc = 0; kc < KCH; ++kc) load_w(&maps.wp, kc * BK, 0, C * BK * 2);
                 }
-                mbar_wait(x_empty, par ^ 1);
-                mbar_expect_tx(x_full, XB);
-                for (int kc = 0; kc < KCH; ++kc) tma_load_2d(&maps.x, x_full, sX + kc * XCH, kc * BK, row0);
+                waited = true;
+                load_act(&maps.x, x_full, x_empty, sX, row0, par);
                 g1w(0);
                 if (NCH > 1) g1w(1);
                 for (int j = 0; j < NCH; ++j) {
@@ -220,11 +238,13 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
         const uint32_t aX = smem_u32(sX), aATT = smem_u32(sATT), aH = smem_u32(sH), aW = smem_u32(sW);
         for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
             if (PROJ) {
+                if (lane == 0) FTL(3, 10, 0);
                 mbar_wait(att_full, par);
                 tc_fence_after();
                 for (int kc = 0; kc < KCH; ++kc) {
                     mbar_wait(&w_full[ws], wph);
                     tc_fence_after();
+                    if (lane == 0) FTL(3, 11, kc);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
@@ -236,7 +256,9 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
                     __syncwarp();
                     if (++ws == S) { ws = 0; wph ^= 1; }
                 }
+                if (lane == 0) FTL(3, 12, 0);
                 mbar_wait(x1_ready, par);
+                if (lane == 0) FTL(3, 13, 0);
             } else {
                 mbar_wait(x_full, par);
             }
@@ -244,8 +266,10 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
             auto g1 = [&](int j) {
                 const uint32_t td = tmem_base + Cfg::D1COL + (uint32_t)((j & 1) * HCH);
                 for (int kc = 0; kc < KCH; ++kc) {
+                    if (lane == 0) FTL(3, 20, j);
                     mbar_wait(&w_full[ws], wph);
                     tc_fence_after();
+                    if (lane == 0) FTL(3, 21, j);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
@@ -260,9 +284,12 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
             };
             auto g2 = [&](int j) {
                 for (int s2 = 0; s2 < HSUB; ++s2) {
+                    if (lane == 0) FTL(3, 30, j);
                     mbar_wait(&h_full[hb], hph);
+                    if (lane == 0) FTL(3, 31, j);
                     mbar_wait(&w_full[ws], wph);
                     tc_fence_after();
+                    if (lane == 0) FTL(3, 32, j);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
@@ -284,7 +311,7 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
                 if (j + 2 < NCH) g1(j + 2);
             }
         }
-    } else {
+    } else if (warp < 18) {
         // ===================== epilogue warps 2..17 =====================
         const int q = (warp - 2) >> 2;        // column quarter
         const int g = warp & 3;               // TMEM lane group this warp may read
@@ -293,24 +320,31 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
         int hb = 0;
         uint32_t hph = 0, par = 0, d1use[2] = {0, 0};
         for (int tile = first; tile < p.tiles; tile += stride, par ^= 1) {
+            const bool tle = warp == 2 && lane == 0;
+            if (tle) FTL(4, 40, 0);
             mbar_wait(x_full, par);
+            if (tle) FTL(4, 41, 0);
             if (PROJ) {
                 // ---- E0: x1 = att.Wp^T + bp + x, in place
                 mbar_wait(d0_full, par);
+                if (tle) FTL(4, 42, 0);
                 tc_fence_after();
                 epi_residual_inplace<C>(tlane + Cfg::D1COL, sX, sBias, r, q);
                 tc_fence_before();
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(x1_ready);
+                if (tle) FTL(4, 43, 0);
             }
             // ---- E1: hidden chunks
 #pragma unroll 1
             for (int j = 0; j < NCH; ++j) {
                 const int b = j & 1;
+                if (tle) FTL(4, 50, j);
                 mbar_wait(&d1_full[b], d1use[b] & 1);
                 ++d1use[b];
                 tc_fence_after();
+                if (tle) FTL(4, 51, j);
 #pragma unroll 1
                 for (int s2 = 0; s2 < HSUB; ++s2) {
                     constexpr int CPW = BK / 4;     // columns per warp in a sub-chunk: 16 (BK=64) or 8 (BK=32)
@@ -334,7 +368,9 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
                     }
 #pragma unroll
                     for (int k = 0; k < CPW; ++k) v[k] = gelu_erf(v[k]);
+                    if (tle) FTL(4, 52, s2);
                     mbar_wait(&h_empty[hb], hph ^ 1);     // the G2 MMAs that read this ring slot have retired
+                    if (tle) FTL(4, 53, s2);
 #pragma unroll
                     for (int pc = 0; pc < CPW / 8; ++pc) {
                         __align__(16) __half2 o[4];
@@ -350,22 +386,26 @@ __global__ void __launch_bounds__(FM_THREADS, 1) swin_mlp_fused_kernel(const __g
                 }
             }
             // ---- E2: x = D2 + b2 + x1, in place, then TMA store
+            if (tle) FTL(4, 60, 0);
             mbar_wait(d2_full, par);
             tc_fence_after();
+            if (tle) FTL(4, 61, 0);
             epi_residual_inplace<C>(tlane + Cfg::D2COL, sX, sBias + 3 * C, r, q);
             tc_fence_before();
             fence_async_smem();
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (warp == 2 && lane == 0) {
-                const int row0 = tile * 128;
-                for (int kc = 0; kc < KCH; ++kc) tma_store_2d(&maps.x, sX + kc * XCH, kc * BK, row0);   // rows >= T are clipped
+            if (warp < 2 + KCH && lane == 0) {
+                // one K-chunk per storing warp (bulk ops of one warp run one after the other); rows >= T are clipped
+                const int kc = warp - 2;
+                tma_store_2d(&maps.x, sX + kc * XCH, kc * BK, tile * 128);
                 tma_store_commit();
                 tma_store_wait_read();
                 mbar_arrive(x_empty);
+                if (tle) FTL(4, 62, 0);
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -395,6 +435,7 @@ static int launch_mlp(cudaStream_t st, const FusedMlp& f) {
     FusedMlpParams p;
     p.tiles = (int)((f.T + 127) / 128);
     p.bp = f.bp; p.b1 = f.b1; p.b2 = f.b2;
+    p.tl = g_timeline;
     const size_t smem = Cfg::smem_bytes(PROJ);
     if (ensure_dyn_smem((const void*)swin_mlp_fused_kernel<C, PROJ>, smem)) return 1;
     int grid = device_sm_count();
@@ -435,5 +476,23 @@ extern "C" int nb200_swin_mlp_fused_f16(void* x, const void* att, long long T, i
     FusedMlp f;
     f.x = (__half*)x; f.att = (const __half*)att; f.T = T; f.C = C;
     f.wp = (const __half*)wp; f.bp = bp; f.w1 = (const __half*)w1; f.b1 = b1; f.w2 = (const __half*)w2; f.b2 = b2;
-    return swin_mlp_fused((cudaStream_t)stream, f);
+    cudaStream_t st = (cudaStream_t)stream;
+    // nb200_tune_set(11, 1): the one-CTA-per-SM kernel; default: the half-SM kernel (two CTAs per SM) where it applies
+    // (C = 96 with or without att needs the proj operands: without att it falls back; C = 192 only without att)
+    const bool half_sm = g_tune[11] == 0 && ((C == 192 && !att) || (C == 96 && att));
+    if (!half_sm) return swin_mlp_fused(st, f);
+    NB_CHECK(C == 96 || C == 192, "C must be 96 or 192");
+    const int bk = C == 192 ? 64 : 32;
+    __half *w1cm = nullptr, *wpcm = nullptr;
+    NB_CUDA(cudaMallocAsync((void**)&w1cm, (size_t)2 * C * C * 2, st));
+    int rc = pack_chunk_major(st, f.w1, w1cm, 2 * C, C, bk);
+    if (!rc && att) {
+        NB_CUDA(cudaMallocAsync((void**)&wpcm, (size_t)C * C * 2, st));
+        rc = pack_chunk_major(st, f.wp, wpcm, C, C, bk);
+    }
+    f.w1_cm = w1cm; f.wp_cm = wpcm;
+    if (!rc) rc = swin_mlp_fused2(st, f);
+    cudaFreeAsync(w1cm, st);
+    if (wpcm) cudaFreeAsync(wpcm, st);
+    return rc;
 }

@@ -323,7 +323,9 @@ __device__ __forceinline__ float shuffled_px(const __half* __restrict__ yb, int 
     return __half2float(yb[((size_t)ty * Ws + tx) * cs + c * r * r + dy * r + dx]);
 }
 
-__global__ void __launch_bounds__(256) to_image_kernel(const __half* __restrict__ y, __half* __restrict__ z, int n, int Hs,
+// z: fp16 for down == 1 (what the reference's module returns under autocast), fp32 for the downscaled models (the reference
+// resizes `z.float()` and returns fp32, swin_unet.py:366-379)
+__global__ void __launch_bounds__(256) to_image_kernel(const __half* __restrict__ y, void* __restrict__ z, int n, int Hs,
                                                        int Ws, int cs, int r, int down) {
     const int S_full = Hs * r, S = S_full / down;
     const size_t total = (size_t)n * 3 * S * S;
@@ -351,7 +353,8 @@ __global__ void __launch_bounds__(256) to_image_kernel(const __half* __restrict_
         }
         v = clamp01(acc);
     }
-    z[i] = __float2half_rn(v);
+    if (down == 1) reinterpret_cast<__half*>(z)[i] = __float2half_rn(v);
+    else reinterpret_cast<float*>(z)[i] = v;
 }
 
 // r=4, down=1 fast path: one thread per token reads its 48 contiguous channels (6 x 16 B) and writes, for each
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(256) to_image_r4_kernel(const __half* __restri
 // per-column tap tables (ATen upsample_bicubic2d_aa weights incl. border renormalisation): 2*4*down FMAs per output
 // instead of (4*down)^2 taps with index arithmetic each.  Same summation order as ATen (horizontal first).
 template <int DOWN>
-__global__ void __launch_bounds__(256) to_image_down_kernel(const __half* __restrict__ y, __half* __restrict__ z, int Hs, int Ws) {
+__global__ void __launch_bounds__(256) to_image_down_kernel(const __half* __restrict__ y, float* __restrict__ z, int Hs, int Ws) {
     constexpr int NT = 4 * DOWN, TO = 64 / DOWN, IN = TO * DOWN + NT;   // taps, output tile, staged input side
     __shared__ float sP[IN][IN + 1];
     __shared__ float sH[IN][TO + 1];
@@ -455,24 +458,24 @@ __global__ void __launch_bounds__(256) to_image_down_kernel(const __half* __rest
 #pragma unroll
         for (int k = 0; k < NT; ++k)
             if (k < sz) acc += sH[base + k][ox] * sWy[oy][k];
-        z[(((size_t)b * 3 + c) * S + Y0 + oy) * S + X0 + ox] = __float2half_rn(clamp01(acc));
+        z[(((size_t)b * 3 + c) * S + Y0 + oy) * S + X0 + ox] = clamp01(acc);
     }
 }
 
-int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws, int cs, int r, int down) {
+int to_image(cudaStream_t st, const __half* y, void* z, int n, int Hs, int Ws, int cs, int r, int down) {
     NB_CHECK(down == 1 || down == 2 || down == 4, "downscale must be 1, 2 or 4");
     NB_CHECK(Hs == Ws && (Hs * r) % down == 0, "bad ToImage geometry");
     const size_t total = (size_t)n * 3 * (Hs * r / down) * (Ws * r / down);
     ProfScope ps(st, PC_TOIMG, (double)n * Hs * Ws * cs * 2 + (double)total * 2);
     if (r == 4 && down == 1 && cs == 48) {
         const size_t tokens = (size_t)n * Hs * Ws;
-        to_image_r4_kernel<<<(unsigned)cdiv64(tokens, 256), 256, 0, st>>>(y, z, n, Hs, Ws);
+        to_image_r4_kernel<<<(unsigned)cdiv64(tokens, 256), 256, 0, st>>>(y, (__half*)z, n, Hs, Ws);
     } else if (r == 4 && cs == 48 && down == 2) {
         const int S = Hs * 2;
-        to_image_down_kernel<2><<<dim3(cdiv(S, 32), cdiv(S, 32), n * 3), 256, 0, st>>>(y, z, Hs, Ws);
+        to_image_down_kernel<2><<<dim3(cdiv(S, 32), cdiv(S, 32), n * 3), 256, 0, st>>>(y, (float*)z, Hs, Ws);
     } else if (r == 4 && cs == 48 && down == 4) {
         const int S = Hs;
-        to_image_down_kernel<4><<<dim3(cdiv(S, 16), cdiv(S, 16), n * 3), 256, 0, st>>>(y, z, Hs, Ws);
+        to_image_down_kernel<4><<<dim3(cdiv(S, 16), cdiv(S, 16), n * 3), 256, 0, st>>>(y, (float*)z, Hs, Ws);
     } else {
         to_image_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(y, z, n, Hs, Ws, cs, r, down);
     }

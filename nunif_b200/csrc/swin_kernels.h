@@ -9,5 +9,6 @@ int build_bias_frag(cudaStream_t st, const float* table_121x6, float* frag);
 // qkv: three dense planes q | k | v, each [B][H][W][C], `plane` elements apart
 int window_attention(cudaStream_t st, const __half* qkv, const float* bias_frag, __half* out, int B, int H, int W, int C,
                      int shift, size_t plane);
-int to_image(cudaStream_t st, const __half* y, __half* z, int n, int Hs, int Ws, int cs, int r, int down);
+// z: fp16 [n][3][S][S] for down == 1, fp32 for down in {2, 4}
+int to_image(cudaStream_t st, const __half* y, void* z, int n, int Hs, int Ws, int cs, int r, int down);
 }  // namespace nb200

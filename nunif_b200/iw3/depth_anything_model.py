@@ -8,8 +8,10 @@ csrc/depth_kernels.cu.  ``infer`` keeps the reference's signature and output con
 float32 on ``x.device``, larger = nearer.
 """
 import ctypes
+from os import path
 import torch
 from .. import _lib
+from .base_depth_model import BaseDepthModel, HUB_MODEL_DIR
 from .depth_anything_preprocess import batch_preprocess
 from .dilation import dilate_edge, edge_dilation_is_enabled
 
@@ -89,38 +91,67 @@ def batch_infer(model, im, flip_aug=True, low_vram=False, enable_amp=False, outp
     return z.to(output_device)
 
 
-class DepthAnythingModel:
-    """BaseDepthModel-shaped wrapper (iw3/base_depth_model.py) around a DepthAnythingNet."""
+MODEL_FILES = {   # depth_anything_model.py:37-42 (the relative-depth V2 checkpoints)
+    "Any_V2_S": path.join(HUB_MODEL_DIR, "checkpoints", "depth_anything_v2_vits.pth"),
+    "Any_V2_B": path.join(HUB_MODEL_DIR, "checkpoints", "depth_anything_v2_vitb.pth"),
+    "Any_V2_L": path.join(HUB_MODEL_DIR, "checkpoints", "depth_anything_v2_vitl.pth"),
+}
+
+
+class DepthAnythingModel(BaseDepthModel):
+    """iw3/depth_anything_model.py:185-281 on the engine: the full BaseDepthModel surface (load / infer / EMA normaliser)."""
 
     def __init__(self, model_type="Any_V2_S"):
         if model_type not in ENCODER_OF:
             raise ValueError(f"the B200 engine implements {list(ENCODER_OF)} (Depth-Anything-V2 relative-depth models)")
-        self.model_type = model_type
-        self.model = None
-        self.device = None
-        self.limit_resolution = False
-
-    def load_state_dict(self, state_dict, gpu=0, resolution=None, limit_resolution=False):
-        """The reference downloads the checkpoint through torch.hub (depth_anything_model.py:223-230); here the caller
-        passes the same state_dict (e.g. torch.load of depth_anything_v2_vits.pth)."""
-        self.device = torch.device(f"cuda:{gpu}") if isinstance(gpu, int) else torch.device(gpu)
-        self.model = DepthAnythingNet(state_dict, self.device, encoder=ENCODER_OF[self.model_type])
-        lb = resolution or 392                                        # :232-235
-        if lb % 14 != 0:
-            lb += 14 - lb % 14
-        self.model.prep_lower_bound = lb
-        self.limit_resolution = limit_resolution
-        return self
-
-    def is_metric(self):
-        return False
+        super().__init__(model_type)
 
     @classmethod
     def get_name(cls):
         return "DepthAnything"
 
+    @classmethod
+    def supported(cls, model_type):
+        return model_type in ENCODER_OF
+
+    @classmethod
+    def get_model_path(cls, model_type):
+        return MODEL_FILES[model_type]
+
+    def is_metric(self):
+        return False
+
+    def _wrap(self, state_dict, resolution, device):
+        net = DepthAnythingNet(state_dict, device, encoder=ENCODER_OF[self.model_type])
+        lb = resolution or 392                                        # :232-235 (GUI 512 -> 518)
+        if lb % 14 != 0:
+            lb += 14 - lb % 14
+        net.prep_lower_bound = lb
+        return net
+
+    def load_model(self, model_type, resolution=None, device=None):
+        """The reference builds the module through torch.hub and lets it download its weights (:186-238); here the same
+        checkpoint file is read from ``get_model_path(model_type)``."""
+        ckpt = self.get_model_path(model_type)
+        if not path.exists(ckpt):
+            raise FileNotFoundError(f"{ckpt} not found (nunif_b200 does not download checkpoints)")
+        return self._wrap(torch.load(ckpt, map_location="cpu", weights_only=True), resolution, device)
+
+    def load_state_dict(self, state_dict, gpu=0, resolution=None, limit_resolution=False):
+        """``load`` from an in-memory state_dict with the upstream key names (tests, bench: seeded weights)."""
+        from .base_depth_model import _device_of
+        self.device = _device_of(gpu)
+        self.limit_resolution = limit_resolution
+        self.model = self._wrap(state_dict, resolution, self.device)
+        return self
+
     def infer(self, x, tta=False, low_vram=False, enable_amp=True, edge_dilation=0, depth_aa=False, **kwargs):
         """depth_anything_model.py:241-253."""
+        if not enable_amp:
+            raise NotImplementedError("nunif_b200 implements the reference's CUDA autocast (fp16) forward only")
+        if not torch.is_tensor(x):
+            import numpy as np
+            x = torch.from_numpy(np.asarray(x, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0).to(self.device)
         _lib.require_cuda(x, "x")
         if depth_aa:
             raise NotImplementedError("depth_aa is not implemented by the B200 engine")

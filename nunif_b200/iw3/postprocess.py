@@ -1,6 +1,7 @@
 """Mirror of iw3/utils.py:394-487 (postprocess_padding, postprocess_image): IPD / letterbox padding, half-SBS and
-half-TB squeeze, anaglyph, SBS / top-bottom / cross-eyed layout, max-output-size resize.  VR180 (equirectangular
-projection) is not implemented."""
+half-TB squeeze, VR180 equirectangular projection (iw3/equirectangular.py:7-40), anaglyph, SBS / top-bottom / cross-eyed
+layout, max-output-size resize."""
+import ctypes
 import torch
 import torch.nn.functional as F
 from .. import _lib
@@ -18,6 +19,19 @@ def resize_bicubic_aa(x, size, clamp=False):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().nb200_resize_bicubic_aa(_lib.ptr(xf), planes, H, W, oh, ow, 1 if clamp else 0, _lib.ptr(out),
                                                       _lib.stream_ptr(x.device)))
+    return out
+
+
+def equirectangular_projection(c, device=None):
+    """iw3/equirectangular.py:7-40: CHW float CUDA tensor -> VR180 view (csrc/postprocess.cu equirect_kernel)."""
+    _lib.require_cuda(c, "c")
+    cf = c.float().contiguous()
+    C, H, W = cf.shape
+    oh, ow = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().nb200_equirectangular_size(H, W, ctypes.byref(oh), ctypes.byref(ow)))
+    out = torch.empty((C, oh.value, ow.value), dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device):
+        _lib.check(_lib.lib().nb200_equirectangular(_lib.ptr(cf), C, H, W, _lib.ptr(out), _lib.stream_ptr(c.device)))
     return out
 
 
@@ -64,7 +78,8 @@ def postprocess_image(left_eye, right_eye, args):
     if g("pad") is not None or g("pad_mode") == "16:9":
         left_eye, right_eye = postprocess_padding(left_eye, right_eye, pad=g("pad"), pad_mode=g("pad_mode"))
     if g("vr180", False):
-        raise NotImplementedError("vr180 (equirectangular projection) is not implemented by the B200 engine")
+        left_eye = equirectangular_projection(left_eye)
+        right_eye = equirectangular_projection(right_eye)
     elif g("half_sbs", False) or g("half_rgbd", False):
         left_eye = resize_bicubic_aa(left_eye, (left_eye.shape[1], left_eye.shape[2] // 2))
         right_eye = resize_bicubic_aa(right_eye, (right_eye.shape[1], right_eye.shape[2] // 2))

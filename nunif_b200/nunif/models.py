@@ -107,8 +107,8 @@ class B200I2IModel:
 
     @torch.no_grad()
     def __call__(self, x):
-        """model(minibatch): x B,3,T,T float/half in [0,1] on self.device -> B,3,S,S fp16
-        (what the reference returns under CUDA autocast)."""
+        """model(minibatch): x B,3,T,T float/half in [0,1] on self.device -> B,3,S,S in the dtype the reference returns under CUDA
+        autocast: fp16 for the native models, fp32 for the 4x-derived 2x / 1x models (they resize ``z.float()``)."""
         _lib.require_cuda(x, "x")
         if x.device != self.device:
             raise RuntimeError(f"input is on {x.device} but the model's packed weights live on {self.device}")
@@ -117,7 +117,7 @@ class B200I2IModel:
         xh = torch.zeros((B, T, T, 8), device=x.device, dtype=torch.float16)
         xh[..., :3] = x.permute(0, 2, 3, 1)
         S = T * self.i2i_scale - 2 * self.i2i_offset
-        z = torch.empty((B, 3, S, S), device=x.device, dtype=torch.float16)
+        z = torch.empty((B, 3, S, S), device=x.device, dtype=torch.float16 if self._downscale == 1 else torch.float32)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().nb200_model_forward(self._h, _lib.ptr(xh), B, T, self._downscale, _lib.ptr(z),
                                                       _lib.stream_ptr(x.device)))

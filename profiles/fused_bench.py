@@ -64,11 +64,24 @@ def main():
             gemm(x, w1, b1, 2, hid)
             gemm(hid, w2, b2, 0, x, res=x)
 
-        tf, tn, tu = timeit(fused), timeit(fused_noproj), timeit(unfused)
+        def half_sm():
+            # what the model runs: C = 96 proj fused in the half-SM kernel; C = 192 proj GEMM + half-SM MLP
+            if C == 192:
+                gemm(att, wp, bp, 0, x, res=x)
+                fused_noproj()
+            else:
+                fused()
+
+        L.nb200_tune_set(11, 1)
+        tf, tn = timeit(fused), timeit(fused_noproj)
+        L.nb200_tune_set(11, 0)
+        th, tu = timeit(half_sm), timeit(unfused)
+        th_mlp = timeit(fused_noproj) if C == 192 else None
         flop = 2.0 * T * C * C * 5
-        out[f"mlp_T{T}_C{C}"] = dict(fused_us=tf, fused_noproj_us=tn, unfused_us=tu, fused_tflops=flop / tf / 1e6,
-                                      hbm_floor_us=T * C * 2 * 3 / 6558e3)
-        print(f"mlp T={T} C={C}: fused {tf:.1f} us ({flop / tf / 1e6:.0f} TF/s), no-proj {tn:.1f} us, unfused {tu:.1f} us", flush=True)
+        out[f"mlp_T{T}_C{C}"] = dict(one_cta_fused_us=tf, one_cta_noproj_us=tn, half_sm_path_us=th, half_sm_mlp_only_us=th_mlp, unfused_us=tu,
+                                      half_sm_tflops=flop / th / 1e6, hbm_floor_us=T * C * 2 * 3 / 6558e3)
+        print(f"mlp T={T} C={C}: half-SM path {th:.1f} us ({flop / th / 1e6:.0f} TF/s; mlp-only kernel {th_mlp}), one-CTA fused {tf:.1f} us, "
+              f"one-CTA no-proj {tn:.1f} us, unfused {tu:.1f} us", flush=True)
     for B, H, C in [(16, 240, 192), (16, 240, 96), (16, 120, 192), (16, 60, 192)]:
         g = torch.Generator().manual_seed(2)
         T = B * H * H

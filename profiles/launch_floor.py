@@ -11,6 +11,8 @@ from nunif_b200.nunif.models import create_model  # noqa: E402
 
 lib = _lib.lib()
 dev = "cuda:0"
+for k, v in (kv.split("=") for kv in os.environ.get("NB200_TUNE", "").split(",") if kv):   # e.g. NB200_TUNE=11=1,10=0
+    lib.nb200_tune_set(int(k), int(v))
 which = sys.argv[1] if len(sys.argv) > 1 else "swin4x"
 if which == "upcunet":
     m = create_model("waifu2x.upcunet", synth.upcunet_state_dict(0), dev)

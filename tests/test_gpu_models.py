@@ -14,24 +14,35 @@ DEV = "cuda:0"
 TOL = 1e-3        # north_star: max-abs 1e-3 vs the reference output
 
 
+def q8_mismatch(a, b):
+    """Fraction of samples whose 8-bit quantisation (x*255 round, what an image file holds) differs."""
+    if a.numel() > (1 << 24):
+        a, b = a.to(DEV), b.to(DEV)
+    elif a.device != b.device:
+        a, b = a.cpu(), b.cpu()
+    qa, qb = (a.float() * 255.0).round().clamp(0, 255), (b.float() * 255.0).round().clamp(0, 255)
+    return float((qa != qb).sum(dtype=torch.float64) / qa.numel())
+
+
 def check(tag, z, golden_fp32, z_amp):
-    """Parity criterion.  e_ref = error of the reference's OWN CUDA path (oracle under fp16
-    autocast) against the reference's CPU fp32 output on the same inputs: that is the noise floor of "the reference
-    output" in fp16.  We require  max|ours - fp32 reference| <= max(TOL, 1.5*e_ref)  (never worse than the reference's
-    own fp16 path, and within 1e-3 wherever fp16 allows it), a mean error < TOL/2 and agreement with the autocast
-    path to the same bound."""
+    """Parity criterion.  e_ref = error of the reference's OWN CUDA path (oracle under fp16 autocast on
+    this GPU) against the fp32 reference output on the same inputs: the noise floor of "the reference output" in fp16.
+    The engine must not be worse than that path:  mean and p99.9 of |ours - fp32| <= 1.0 x the autocast figures (or the
+    north-star 1e-3 / 5e-4 where fp16 allows it); only the max - a noisy statistic over 1e5..1e8 samples - gets 1.5 x.
+    Also logged and bounded: the fraction of samples whose 8-bit value differs from the fp32 reference (ours vs autocast)."""
     ours32 = stats(z, golden_fp32)
     ref32 = stats(z_amp, golden_fp32)
     oursamp = stats(z, z_amp)
+    q_ours, q_ref, q_cross = q8_mismatch(z, golden_fp32), q8_mismatch(z_amp, golden_fp32), q8_mismatch(z, z_amp)
     log_metric(tag, ours_vs_fp32=ours32["max"], refamp_vs_fp32=ref32["max"], ours_vs_refamp=oursamp["max"],
-               ours_mean=ours32["mean"], refamp_mean=ref32["mean"], ours_frac_gt_1e3=ours32["frac_gt_1e3"],
-               refamp_frac_gt_1e3=ref32["frac_gt_1e3"])
-    # 1.5x slack: two fp16 evaluation orders never agree exactly, and the max over ~1e5-1e6 pixels is a noisy statistic
-    bound = max(TOL, 1.5 * ref32["max"])
-    assert ours32["max"] <= bound, (tag, ours32, ref32)
-    assert ours32["mean"] <= max(TOL / 2, 1.25 * ref32["mean"]), (tag, ours32, ref32)
-    assert ours32["p999"] <= max(TOL, 1.25 * ref32["p999"]), (tag, ours32, ref32)
-    assert oursamp["max"] <= 2 * bound, (tag, oursamp, ref32)
+               ours_mean=ours32["mean"], refamp_mean=ref32["mean"], ours_p999=ours32["p999"], refamp_p999=ref32["p999"],
+               ours_frac_gt_1e3=ours32["frac_gt_1e3"], refamp_frac_gt_1e3=ref32["frac_gt_1e3"],
+               q8_ours_vs_fp32=q_ours, q8_refamp_vs_fp32=q_ref, q8_ours_vs_refamp=q_cross)
+    assert ours32["mean"] <= max(TOL / 2, 1.0 * ref32["mean"]), (tag, ours32, ref32)
+    assert ours32["p999"] <= max(TOL, 1.0 * ref32["p999"]), (tag, ours32, ref32)
+    assert ours32["max"] <= max(TOL, 1.5 * ref32["max"]), (tag, ours32, ref32)
+    assert oursamp["max"] <= 2 * max(TOL, 1.5 * ref32["max"]), (tag, oursamp, ref32)
+    assert q_ours <= max(1e-3, 1.25 * q_ref), (tag, q_ours, q_ref)
 
 
 def amp(fn, *a):
@@ -253,3 +264,76 @@ def test_state_dict_is_strict():
         create_model("waifu2x.swin_unet_4x", bad, DEV)
     with pytest.raises(ValueError):
         create_model("waifu2x.nope", sd, DEV)
+
+
+# ---------------------------------------------------------------------------------------------
+# parity AT THE BENCHMARKED CONFIGURATION (bench.py: tile 256, batch 16, 4K frame)
+# ---------------------------------------------------------------------------------------------
+def _fp32_ref(fn, *a):
+    """The oracle on the GPU in plain fp32 (TF32 off) - the same arithmetic as the CPU goldens, at sizes the CPU cannot reach."""
+    sdc = {k: v.to(DEV) for k, v in a[0].items()}
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return fn(sdc, *a[1:]).float()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_swin4x_forward_at_bench_shape():
+    """16 tiles of 256x256 through swin_unet_4x: the launch shapes of the bench (M = 921 600 tokens, the fused kernels' full
+    persistent grids), against the fp32 oracle and the autocast oracle on the same GPU."""
+    from nunif_b200.nunif.models import create_model
+    sd = synth.swin_unet_state_dict(0, 4)
+    m = create_model("waifu2x.swin_unet_4x", sd, DEV)
+    x = torch.stack([synth.synth_image(300 + i, 3, 256, 256, smooth=(i % 2 == 0)) for i in range(16)]).to(DEV)
+    z = m(x).float()
+    want = _fp32_ref(osw.swin_unet_forward, sd, x, 4)
+    check("swin4x_forward_256x16", z, want, amp(osw.swin_unet_forward, sd, x, 4))
+    z2 = m.to_2x()(x).float()
+    want2 = _fp32_ref(osw.swin_unet_forward, sd, x, 4, 2)
+    check("swin4x_to_2x_forward_256x16", z2, want2, amp(osw.swin_unet_forward, sd, x, 4, 2))
+
+
+def test_upcunet_forward_at_bench_shape():
+    from nunif_b200.nunif.models import create_model
+    sd = synth.upcunet_state_dict(0)
+    m = create_model("waifu2x.upcunet", sd, DEV)
+    x = torch.stack([synth.synth_image(400 + i, 3, 256, 256, smooth=(i % 2 == 0)) for i in range(16)]).to(DEV)
+    z = m(x).float()
+    check("upcunet_forward_256x16", z, _fp32_ref(ocu.cunet_forward, sd, x, True), amp(ocu.cunet_forward, sd, x, True))
+
+
+@pytest.mark.parametrize("down", [1, 2])
+def test_swin4x_render_4k_frame(down):
+    """The benchmarked frame itself: 3x2160x3840 -> 4x (down=1, bench headline) and the 4x-derived 2x model (down=2, the
+    north-star `to_2x` path), tile 256 / batch 16, whole output compared with the oracle's tiled render (reference tiling loop
+    + fp32 / autocast oracle model on the GPU)."""
+    from nunif_b200.nunif.models import create_model
+    from nunif_b200.nunif.render import tiled_render
+    sd = synth.swin_unet_state_dict(0, 4)
+    m = create_model("waifu2x.swin_unet_4x", sd, DEV)
+    model = m if down == 1 else m.to_2x()
+    img = synth.synth_image(1000, 3, 2160, 3840, smooth=False)
+    with torch.no_grad():
+        y = tiled_render(img.to(DEV), model, tile_size=256, batch_size=16)
+    sdc = {k: v.to(DEV) for k, v in sd.items()}
+    scale, offset, blend = (4, 32, 16) if down == 1 else (2, 16, 8)
+
+    def fp32_model(b):
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                return osw.swin_unet_forward(sdc, b.to(DEV), 4, down).float().cpu()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    def amp_model(b):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return osw.swin_unet_forward(sdc, b.to(DEV), 4, down).float().cpu()
+    want = osb.tiled_render(img, fp32_model, scale, offset, blend, 256, 16)
+    y_amp = osb.tiled_render(img, amp_model, scale, offset, blend, 256, 16)
+    assert y.shape == want.shape == (3, 2160 * scale, 3840 * scale)
+    check(f"swin4x_render_4k_down{down}", y, want, y_amp)

@@ -37,8 +37,30 @@ def test_postprocess_image_golden():
         s = stats(got, want)
         log_metric("postprocess_" + name, **s)
         assert s["max"] < 2e-5, (name, s)
-    with pytest.raises(NotImplementedError):
-        postprocess_image(l, r, types.SimpleNamespace(vr180=True))
+
+
+def test_vr180_equirectangular_golden_and_oracle():
+    """iw3/equirectangular.py through the reference-generated golden (tests/golden/postprocess.npz vr180_l) and, for a
+    non-square odd-sized frame, the numpy oracle; then the vr180 branch of postprocess_image."""
+    from nunif_b200.iw3 import equirectangular_projection, postprocess_image
+    g = load_golden("postprocess")
+    l, r = t(g["l"], DEV).clamp(0, 1), t(g["r"], DEV).clamp(0, 1)
+    got = equirectangular_projection(l)
+    want = t(g["vr180_l"])
+    assert tuple(got.shape) == tuple(want.shape)
+    s = stats(got, want)
+    log_metric("vr180_golden", **s)
+    assert s["max"] < 2e-4 and s["mean"] < 2e-6, s
+    x = synth.synth_image(9, 3, 75, 133)
+    got = equirectangular_projection(x.to(DEV))
+    want = torch.from_numpy(opp.equirectangular_projection(x.numpy()))
+    assert tuple(got.shape) == tuple(want.shape)
+    s = stats(got, want)
+    log_metric("vr180_oracle_odd", **s)
+    assert s["max"] < 2e-4 and s["mean"] < 2e-6, s
+    sbs = postprocess_image(l, r, types.SimpleNamespace(vr180=True))
+    assert sbs.shape[1] == got.shape[1] * 0 + equirectangular_projection(l).shape[1] and sbs.shape[2] == 2 * equirectangular_projection(l).shape[2]
+    assert torch.equal(sbs[:, :, :sbs.shape[2] // 2], equirectangular_projection(l))
 
 
 def test_half_sbs_1080p_against_oracle():

@@ -26,6 +26,14 @@ def log_metric(name, **kv):
 
 
 def stats(got, want):
+    """max / mean / 99.9th percentile of |got - want| and the fraction above 1e-3.  Small tensors: float64 on the CPU; large ones
+    (whole 4K x 4 frames, 4e8 samples) on the GPU in float32 with a float64 mean."""
+    if got.numel() > (1 << 24) and torch.cuda.is_available():
+        dev = got.device if got.is_cuda else (want.device if want.is_cuda else torch.device("cuda:0"))
+        d = (got.to(dev, torch.float32) - want.to(dev, torch.float32)).abs().flatten()
+        k = max(1, int(d.numel() * 0.999))
+        return dict(max=float(d.max()), mean=float(d.sum(dtype=torch.float64) / d.numel()), p999=float(d.kthvalue(k).values),
+                    frac_gt_1e3=float((d > 1e-3).sum(dtype=torch.float64) / d.numel()))
     d = (got.double().cpu() - want.double().cpu()).abs()
     return dict(max=float(d.max()), mean=float(d.mean()), p999=float(d.flatten().kthvalue(max(1, int(d.numel() * 0.999))).values),
                 frac_gt_1e3=float((d > 1e-3).double().mean()))
