@@ -23,6 +23,13 @@ sys.path.insert(0, ROOT)
 
 FRAME = {"4k": (2160, 3840), "1080p": (1080, 1920), "8k": (4320, 7680)}
 TILE, BATCH = 256, 16
+# --workload: (model variant, frame, name in the JSON line).  swin4x_4k is BASELINE.json configs[1] (the headline);
+# swin2x_4k the north-star `to_2x` path on the same frame; swin2x_8k configs[3] (one 8K frame per GPU).
+WORKLOADS = {
+    "swin4x_4k": dict(down=1, frame="4k", text="waifu2x swin_unet/art scale4x"),
+    "swin2x_4k": dict(down=2, frame="4k", text="waifu2x swin_unet/art scale2x (SwinUNet4x.to_2x: 4x network + antialiased bicubic /2)"),
+    "swin2x_8k": dict(down=2, frame="8k", text="waifu2x swin_unet/photo scale2x (SwinUNet4x.to_2x), 8K frame per GPU (configs[3])"),
+}
 SWIN4X_TILE_GFLOP = 155.7           # BASELINE.md section 2 (conv 8.6 + addmm 140.1 + bmm 7.0)
 
 
@@ -158,12 +165,18 @@ def cpu_baseline_object(h, w, ntiles, tiles_per_worker=1):
                          f"to last finish; MP/s = frame MP * {done}/{ntiles} / t"}
 
 
+def _default_frame(args):
+    if args.frame is None:
+        args.frame = WORKLOADS[args.workload]["frame"]
+
+
 def run_reference(args):
     """The reference arm: the reference's algorithm (oracle port; the reference itself is Python with no installable package
     and cannot travel to the GPU box) on ALL host cores - several tile batches at a time, every core busy."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _default_frame(args)
     h, w = FRAME[args.frame]
     ntiles = frame_tiles(h, w)
     ts, cb = [], None
@@ -198,6 +211,7 @@ def run_torch_gpu(args):
     if rank != 0:
         return
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    _default_frame(args)
     h, w = FRAME[args.frame]
     ntiles = frame_tiles(h, w)
     sd = {k: v.to(dev) for k, v in synth.swin_unet_state_dict(0, 4).items()}
@@ -326,26 +340,32 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
     # H2D, uint8->float CHW, depth, warp, SBS, float->uint8 HWC, D2H of the SBS frames
     from nunif_b200.iw3 import hwc_to_chw_float, chw_float_to_hwc
     u8_in = (c.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).cpu().pin_memory()
-    u8_out = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8).pin_memory()
 
-    def e2e():
-        with torch.inference_mode():
-            xf = hwc_to_chw_float(u8_in.to(dev, non_blocking=True))
-            depth = dam.infer(xf, edge_dilation=[2, 1])
-            sbs = stereo_sbs(xf, depth, 2.0, 0.5, method="forward_fill", edge_dilation=0)
-            u8_out.copy_(chw_float_to_hwc(sbs), non_blocking=True)
-    for _ in range(3):
-        e2e()
+    # FrameBatchPipeline (nunif_b200/nunif/video.py): 3-slot ring, H2D | uint8->float, depth, warp, SBS, float->uint8 | D2H on three
+    # streams, frames returned in ticket order - what FrameCallbackPool + per-thread streams do in the reference
+    from nunif_b200.nunif.video import FrameBatchPipeline
+
+    def sbs_callback(xf):
+        depth = dam.infer(xf, edge_dilation=[2, 1])
+        return stereo_sbs(xf, depth, 2.0, 0.5, method="forward_fill", edge_dilation=0)
+    frames_host = [u8_in[i] for i in range(B)]
+    pipe = FrameBatchPipeline(sbs_callback, B, dev, depth=3, copy_output=False)
+    n_frames = B * (iters + 3)
+    done = 0
+    for i in range(3 * B):                      # warm: fills the ring
+        done += len(pipe(frames_host[i % B]))
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        e2e()
-    e1.record()
+    t0 = time.perf_counter()
+    for i in range(iters * B):
+        done += len(pipe(frames_host[i % B]))
+    done += len(pipe.finish())
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    out["e2e_uint8_host_forward_fill"] = {"fps": B / (ms / 1e3), "ms_per_batch": ms, "batch": B,
-                                          "h2d_bytes_per_batch": int(u8_in.numel()), "d2h_bytes_per_batch": int(u8_out.numel())}
+    dt = time.perf_counter() - t0
+    assert done == n_frames, (done, n_frames)
+    out["e2e_uint8_host_forward_fill"] = {"fps": iters * B / dt, "ms_per_batch": dt * 1e3 / iters, "batch": B,
+                                          "h2d_bytes_per_batch": int(u8_in.numel()), "d2h_bytes_per_batch": int(B * H * 2 * W * 3),
+                                          "pipeline": "FrameBatchPipeline depth 3 (copy-in | compute | copy-out streams), host wall clock over "
+                                                      f"{iters} batches incl. the final drain, frames pushed one by one from pinned uint8"}
     return out
 
 
@@ -371,6 +391,28 @@ def bench_8k_downscaled(dev, model4x, iters=2):
         del y
     return {"ms_per_frame": ms, "frames_per_sec": 1e3 / ms, "input_megapixels_per_sec": 4320 * 7680 / 1e6 / (ms / 1e3),
             "tiles": 627, "output_shape": shape, "model_tflops_per_sec": 627 * 155.7 / 1e3 / (ms / 1e3)}
+
+
+def bench_to2x_4k(dev, model4x, x, iters=3):
+    """Secondary: the north-star workload itself - swin_unet/art 2x (the released 2x model IS the 4x network followed by the
+    antialiased bicubic /2, waifu2x/utils.py:128-176) on the same 4K frame, tile 256, batch 16, device-timed."""
+    import torch
+    from nunif_b200.nunif.render import tiled_render
+    m2 = model4x.to_2x()
+    with torch.no_grad():
+        y = tiled_render(x, m2, tile_size=TILE, batch_size=BATCH)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            y = tiled_render(x, m2, tile_size=TILE, batch_size=BATCH)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        shape = tuple(y.shape)
+        del y
+    h, w = x.shape[1], x.shape[2]
+    return {"ms_per_frame": ms, "frames_per_sec": 1e3 / ms, "input_megapixels_per_sec": h * w / 1e6 / (ms / 1e3), "output_shape": shape}
 
 
 def bench_upcunet(dev, lib, x, iters=3):
@@ -438,18 +480,24 @@ def run_b200(args):
     if os.environ.get("NB200_GRAPHS"):
         _lib.check(lib.nb200_tune_set(9, int(os.environ["NB200_GRAPHS"])))   # CUDA-graph replay of the tile-batch forward (A/B)
 
+    wl = WORKLOADS[args.workload]
+    if args.frame is None:
+        args.frame = wl["frame"]
     h, w = FRAME[args.frame]
-    ntiles = frame_tiles(h, w)
+    down = wl["down"]
+    oscale = 4 // down
+    ntiles = frame_tiles(h, w, scale=oscale, offset=32 // down, blend=16 if down == 1 else 4 * down)
     # every rank builds the same container; rank 0's packed weight blob is broadcast once over NCCL
     # (replaces torch.nn.parallel.replicate, nunif/models/data_parallel.py:16,58)
-    model = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), dev)
+    model4x = create_model("waifu2x.swin_unet_4x", synth.swin_unet_state_dict(0, 4), dev)
     if world > 1:
         from nunif_b200 import parallel
-        parallel.broadcast_model_weights(model, src=0)
+        parallel.broadcast_model_weights(model4x, src=0)
+    model = model4x if down == 1 else model4x.to_2x()
     # per-rank frame (weak scaling: one frame per GPU per step), already resident in HBM
     x = synth.synth_image(1000 + rank, 3, h, w, smooth=False).to(dev)
     x_host = synth.synth_image(1000 + rank, 3, h, w, smooth=False).pin_memory()
-    out_host = torch.empty((3, h * 4, w * 4), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((3, h * oscale, w * oscale), dtype=torch.float32).pin_memory()
 
     def step():
         return tiled_render(x, model, tile_size=TILE, batch_size=BATCH)
@@ -505,10 +553,11 @@ def run_b200(args):
             except Exception as e:  # noqa: BLE001
                 torch.cuda.synchronize()
                 return {"error": f"{type(e).__name__}: {e}"}
-        secondaries = rank == 0 and not os.environ.get("NB200_BENCH_MINIMAL")   # (set for the ncu launch-list pass)
+        secondaries = rank == 0 and args.workload == "swin4x_4k" and not os.environ.get("NB200_BENCH_MINIMAL")   # (set for the ncu launch-list pass)
+        to2x = guarded(bench_to2x_4k, dev, model4x, x) if secondaries else None
         iw3 = guarded(bench_iw3, dev, lib, peaks_gbs=load_peaks()[0]["hbm_gbs"]) if secondaries else None
         upc = guarded(bench_upcunet, dev, lib, x) if secondaries else None
-        cfg4 = guarded(bench_8k_downscaled, dev, model) if secondaries else None
+        cfg4 = guarded(bench_8k_downscaled, dev, model4x) if secondaries else None
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -551,15 +600,16 @@ def run_b200(args):
         "metric": "waifu2x_input_megapixels_per_sec", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"waifu2x swin_unet/art scale4x, {args.frame} input 3x{h}x{w}, tile_size=256 batch=16, "
+        "config": {"workload": f"{wl['text']}, {args.frame} input 3x{h}x{w}, tile_size=256 batch=16, "
                                f"{ntiles} tiles/frame, 1 frame/GPU/step",
+                   "workload_key": args.workload,
                    "parallelism": f"frame-parallel x{world} (no data-path collective; NCCL weight broadcast at load)",
                    "weights": "random-init seed 0 (nunif_b200.synth)",
                    "l2": "inputs/activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                    "frames_per_sec": world * args.steps / (ms / 1e3),
-                   "output_megapixels_per_sec": value * 16,
+                   "output_megapixels_per_sec": value * oscale * oscale,
                    "model_tflops_per_sec": world * args.steps * ntiles * SWIN4X_TILE_GFLOP / 1e3 / (ms / 1e3)},
-        "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": 3 * h * w * 4, "d2h_bytes_per_step": 3 * h * w * 16 * 4,
+        "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": 3 * h * w * 4, "d2h_bytes_per_step": 3 * h * w * oscale * oscale * 4,
                 "steps": e2e_steps, "note": "pinned host frame -> tiled_render (nb200_tiled_render_host: H2D, render, output blended and copied back in bands "
                         "of finished tile rows on a side stream) -> pinned host fp32 output; every step moves all bytes"},
         "gpu_launches": int(launches),
@@ -578,6 +628,8 @@ def run_b200(args):
         "roofline_by_class": views,
         "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }
+    if to2x is not None:
+        line["swin_to_2x_4k"] = to2x
     if upc is not None:
         line["upcunet_4k_2x"] = upc
     if cfg4 is not None:
@@ -600,7 +652,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
     ap.add_argument("--compile", action="store_true", help="--impl torch_gpu: wrap the forward in torch.compile")
     ap.add_argument("--cpu-worker", nargs=2, type=int, metavar=("TILES", "THREADS"), help=argparse.SUPPRESS)
-    ap.add_argument("--frame", default="4k", choices=list(FRAME))
+    ap.add_argument("--frame", default=None, choices=list(FRAME), help="frame size (default: the workload's)")
+    ap.add_argument("--workload", default="swin4x_4k", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.cpu_worker:

@@ -71,6 +71,7 @@ constexpr int PG_SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 512 /*bar
 
 // tuning knobs for profiles/gemm_bench.py (nb200_tune_set); defaults are the shipped configuration
 unsigned long long* g_timeline = nullptr;
+std::atomic<int> g_tune_epoch{0};
 int g_tune[16] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG_MAX_STAGES, /*2 grid cap (0 = #SMs)*/ 0, /*3 force gather backward warp*/ 0,
                  /*4 forced BLOCK_N*/ 0, /*5 disable GELU->128 rule*/ 0,
                  /*6 attention smem carveout %*/ 0, /*7 SIMT stem / tail convs*/ 0,
@@ -363,5 +364,6 @@ extern "C" int nb200_debug_timeline(void* dev_buf) {
 extern "C" int nb200_tune_set(int key, int value) {
     NB_CHECK(key >= 0 && key < 16, "bad key");
     g_tune[key] = value;
+    g_tune_epoch.fetch_add(1);   // models drop their captured CUDA graphs (model.cu)
     return 0;
 }

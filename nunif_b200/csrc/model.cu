@@ -21,6 +21,7 @@
 namespace nb200 {
 
 extern int g_tune[16];                 // gemm.cu (nb200_tune_set)
+extern std::atomic<int> g_tune_epoch;  // gemm.cu: bumped by every nb200_tune_set (captured graphs bake the knobs in)
 extern unsigned long long* g_timeline;  // gemm.cu (nb200_debug_timeline)
 
 // ---------------------------------------------------------------------------------------------
@@ -230,6 +231,7 @@ struct nb200_model {
     std::map<GraphKey, cudaGraphExec_t> graphs;
     std::map<GraphKey, int> graph_seen;
     std::map<GraphKey, uint64_t> graph_launches;   // kernel launches one replay stands for (nb200_launch_count)
+    int graph_epoch = 0;                            // g_tune_epoch the cached graphs were captured under
     void clear_graphs() {
         for (auto& kv : graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
         graphs.clear();
@@ -645,6 +647,11 @@ extern "C" int nb200_model_forward(nb200_model* m, const void* x, int n, int til
     // (buffers, shape) has been seen twice; removes most of the inter-kernel launch latency (≈7 % of a 4K frame,
     // profiles/r1/launches_bench_step_summary.txt).  Never while the event profiler or the timeline probe is on.
     if (!g_tune[9] || g_prof_enabled.load(std::memory_order_relaxed) || g_timeline) return eager();
+    if (m->graph_epoch != g_tune_epoch.load()) {            // a tuning knob changed: the captured launch configurations are stale
+        m->clear_graphs();
+        m->graph_epoch = g_tune_epoch.load();
+    }
+    if (m->graph_seen.size() > 1024) m->graph_seen.clear();  // callers that never repeat a (buffers, shape) key
     const nb200_model::GraphKey key{x, z, n, tile_size, downscale};
     auto it = m->graphs.find(key);
     if (it != m->graphs.end()) {
@@ -732,6 +739,10 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     const int z_f32 = downscale > 1;
     const size_t zsz = z_f32 ? 4 : 2;
     const size_t oplane = (size_t)cfg.y_h * cfg.y_w;
+    struct AsyncFree {   // the frame-level scratch goes back to the stream-ordered pool on every exit path
+        cudaStream_t st; float** a; float** b;
+        ~AsyncFree() { if (*a) cudaFreeAsync(*a, st); if (*b) cudaFreeAsync(*b, st); }
+    } scratch_guard{st, &xd, &od};
     NB_CUDA(cudaMallocAsync((void**)&xd, (size_t)C * H * W * 4, st));
     NB_CUDA(cudaMallocAsync((void**)&od, (size_t)C * oplane * 4, st));
     if (m->ensure_frame(xb_elems * 2, (size_t)ntiles * z_tile * zsz)) return 1;
@@ -768,10 +779,7 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     NB_CUDA(cudaEventRecord(ev_end, cs));
     NB_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
     NB_CUDA(cudaEventDestroy(ev_end));
-    cudaFreeAsync(xd, st);
-    cudaFreeAsync(od, st);
-
-    return rc;
+    return rc;   // scratch_guard frees xd / od behind the last copy (stream-ordered)
 }
 
 // DepthAnythingV2.forward (what DepthAnythingModel._forward calls, iw3/depth_anything_model.py:113-119)

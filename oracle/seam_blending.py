@@ -76,10 +76,10 @@ def tiled_render(x, model_fn, scale, offset, blend_size, tile_size, batch_size):
     C, H, W = x.shape
     blend_size = blend_size or 0
     cfg = create_config(H, W, scale, offset, tile_size, blend_size)
-    pixels = torch.zeros((C, cfg["y_buffer_h"], cfg["y_buffer_w"]), dtype=torch.float32)
-    if blend_size > 0:
+    pixels = torch.zeros((C, cfg["y_buffer_h"], cfg["y_buffer_w"]), dtype=torch.float32, device=x.device)   # (the reference keeps
+    if blend_size > 0:                                                                                      #  its buffers on the frame's device)
         weights = torch.zeros_like(pixels)
-        blend_filter = create_blend_filter(scale, offset, tile_size, blend_size, C)
+        blend_filter = create_blend_filter(scale, offset, tile_size, blend_size, C).to(x.device)
     step_in = cfg["input_tile_step"]
     step_out = cfg["output_tile_step"]
     xp = F.pad(x.unsqueeze(0), cfg["pad"], mode="replicate")[0]

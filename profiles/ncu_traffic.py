@@ -20,7 +20,7 @@ WANT = {
     "launch__registers_per_thread": "registers", "launch__grid_size": "grid", "launch__block_size": "block",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
 }
-UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9}
+UNIT = {"us": 1e3, "ns": 1.0, "ms": 1e6, "s": 1e9, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0, "second": 1e9}
 
 
 def num(v):
