@@ -479,6 +479,9 @@ def run_b200(args):
     _lib.check(lib.nb200_check_device(local))
     if os.environ.get("NB200_GRAPHS"):
         _lib.check(lib.nb200_tune_set(9, int(os.environ["NB200_GRAPHS"])))   # CUDA-graph replay of the tile-batch forward (A/B)
+    for kv in filter(None, os.environ.get("NB200_TUNE", "").split(",")):    # A/B knobs of csrc/gemm.cu g_tune, e.g. NB200_TUNE=12=1
+        k, v = kv.split("=")
+        _lib.check(lib.nb200_tune_set(int(k), int(v)))
 
     wl = WORKLOADS[args.workload]
     if args.frame is None:

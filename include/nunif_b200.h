@@ -260,6 +260,11 @@ int nb200_swin_mlp_fused_f16(void* x, const void* att, long long T, int C, const
 int nb200_swin_attn_fused_f16(const void* x, const void* wqkv, const float* bqkv,
                               const float* bias_table, void* att, int B, int H, int W, int C,
                               int shift, void* stream);
+/* The same operator and operands with QK^T and PV on tcgen05 as well (csrc/swin_attn_tc.cu: S and P live in tensor
+ * memory / shared memory, three windows per 128-row UMMA); this is the kernel the model path launches. */
+int nb200_swin_attn_tc_f16(const void* x, const void* wqkv, const float* bqkv,
+                           const float* bias_table, void* att, int B, int H, int W, int C,
+                           int shift, void* stream);
 
 /* Frame-edge conversions (nunif/utils/video.py:218-223 to_tensor, :236-246 from_tensor,
  * iw3/utils.py:274-289 hwc_to_chw_float): x [B][H][W][3] uint8 (bits=8) or uint16 (bits=16)

@@ -78,7 +78,8 @@ int g_tune[16] = {/*0 epilogue quads without residual*/ 4, /*1 max A stages*/ PG
                   /*8 programmatic dependent launch of the GEMMs*/ 1,
                   /*9 CUDA-graph replay of nb200_model_forward*/ 0,
                   /*10 unfused Swin blocks (round-1 launch sequence)*/ 0,
-                  /*11 one-CTA-per-SM fused MLP instead of the half-SM kernel*/ 0, 0, 0, 0, 0};
+                  /*11 one-CTA-per-SM fused MLP instead of the half-SM kernel*/ 0,
+                  /*12 mma.sync attention warps (swin_fused_attn.cu) instead of swin_attn_tc.cu*/ 0, 0, 0, 0};
 
 template <int BN, int BK, bool RES>
 static int launch_p(cudaStream_t st, const GemmMaps& maps, PersistParams& pp, int stages, size_t smem, int grid) {

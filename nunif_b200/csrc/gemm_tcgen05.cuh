@@ -64,20 +64,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// cold path of mbar_wait, kept out of line: the call sites of a warp-specialised kernel are many and instruction-cache space is
+// what those kernels run out of first (profiles/r2/attn_tc_ncu_v7_source.txt: most stalls of the working warps are no-instruction)
+__device__ __noinline__ void mbar_timeout() {
+    printf("nb200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    // bounded spin: a protocol bug traps instead of hanging the GPU
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
+    // try_wait WITH a suspend-time hint: the thread sleeps in hardware until the phase completes (or 20 us pass) instead of
+    // re-issuing the instruction.  Without the hint the default time limit is short and every waiting warp of a warp-specialised
+    // CTA spins in the issue slots of its scheduler: with ~5 waiting warps per scheduler the working warps of swin_attn_tc.cu ran
+    // at ~10 cycles per instruction (profiles/r2/attn_tc_timeline_v5.txt).  Bounded: a protocol bug traps instead of hanging the GPU.
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 18); ++it) {     // (the compiler unrolled this loop 32x at every call site: 2048 try_waits per kernel)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (done) return;
     }
-    printf("nb200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-    __trap();
+    mbar_timeout();
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -192,6 +192,8 @@ struct SwinBlockW {
     size_t fc1_cm = 0, proj_cm = 0;   // chunk-major [K/BK][rows][BK] fp16 copies for swin_fused_mlp2.cu
     size_t table = 0;     // bias in accumulator-fragment order (unfused attention kernel)
     size_t btab = 0;      // bias as [6][36][40] fp32 (fused attention kernel)
+    Lin qkv_tc;           // rows regrouped per 96-column unit for swin_attn_tc.cu
+    size_t btab_tc = 0;   // relative_position_bias_table [121][6] fp32 as stored
     int C = 0, shift = 0;
 };
 
@@ -297,6 +299,15 @@ static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std
                 b.qkv_fused.N = 3 * C; b.qkv_fused.K = C;
                 b.qkv_fused.w = pk.add_f16(wv);
                 b.qkv_fused.b = pk.add_f32(bv);
+                // swin_attn_tc.cu: 96 rows per unit = one head (C = 192) or a head pair (C = 96), [q | k | v] inside
+                for (int pr = 0; pr < 3 * C; ++pr) {
+                    const int src = swin_attn_tc_src_row(pr, C);
+                    memcpy(&wv[(size_t)pr * C], &w[(size_t)src * C], (size_t)C * 4);
+                    bv[pr] = bq[src];
+                }
+                b.qkv_tc.N = 3 * C; b.qkv_tc.K = C;
+                b.qkv_tc.w = pk.add_f16(wv);
+                b.qkv_tc.b = pk.add_f32(bv);
             }
         }
         b.proj = pack_linear(pk, p + ".attn.proj", C, C);
@@ -346,6 +357,7 @@ static void pack_swin_blocks(Packer& pk, std::vector<SwinBlockW>& out, const std
                         tab[((size_t)head * 36 + row) * 40 + col] = 1.4426950408889634f * t[((qy - ky + 5) * 11 + (qx - kx + 5)) * 6 + head];
                     }
             b.btab = pk.add_f32(tab);
+            b.btab_tc = pk.add_f32(std::vector<float>(t, t + 121 * 6));
         }
         pk.mark(p + ".attn.relative_position_index");  // buffer; the kernel recomputes the index (swin_transformer.py:267-279)
         out.push_back(b);
@@ -414,7 +426,9 @@ static int swin_block(cudaStream_t st, const nb200_model* m, const SwinBlockW& w
         FusedAttn fa;
         fa.x = X; fa.att = ATT; fa.B = n; fa.H = H; fa.W = H; fa.C = C; fa.shift = w.shift;
         fa.wqkv = m->at<__half>(w.qkv_fused.w); fa.bqkv = m->at<float>(w.qkv_fused.b); fa.bias_tab = m->at<float>(w.btab);
-        if (swin_attn_fused(st, fa)) return 1;
+        fa.wqkv_tc = m->at<__half>(w.qkv_tc.w); fa.bqkv_tc = m->at<float>(w.qkv_tc.b); fa.bias_tab_tc = m->at<float>(w.btab_tc);
+        // g_tune[12] != 0: the round-2a kernel (mma.sync attention warps) for A/B measurements
+        if (g_tune[12] ? swin_attn_fused(st, fa) : swin_attn_tc(st, fa)) return 1;
         FusedMlp fm;
         fm.x = X; fm.att = ATT; fm.T = T; fm.C = C;
         fm.wp = m->at<__half>(w.proj.w); fm.bp = m->at<float>(w.proj.b);

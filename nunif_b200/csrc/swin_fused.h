@@ -35,7 +35,21 @@ struct FusedAttn {
     const __half* wqkv = nullptr;   // [3C][C], row order (pair, {q,k,v}, head-in-pair, d)
     const float* bqkv = nullptr;    // [3C], same order
     const float* bias_tab = nullptr;
+    // swin_attn_tc.cu: rows ordered (unit, {q,k,v}, head-in-unit, d) with 96 rows per unit (swin_attn_tc_src_row); the bias
+    // is the raw relative_position_bias_table [121][6] fp32
+    const __half* wqkv_tc = nullptr;
+    const float* bqkv_tc = nullptr;
+    const float* bias_tab_tc = nullptr;
 };
 int swin_attn_fused(cudaStream_t st, const FusedAttn& f);
+// the same operator with QK^T and PV on tcgen05 as well (swin_attn_tc.cu); uses the *_tc operands
+int swin_attn_tc(cudaStream_t st, const FusedAttn& f);
+// packed row pr of the tc layout -> row of the reference qkv weight ([q | k | v], head-major inside each)
+__host__ __device__ inline int swin_attn_tc_src_row(int pr, int C) {
+    const int D = C / 6, NHU = 32 / D;
+    const int u = pr / 96, rem = pr % 96;
+    const int m = rem / 32, hh = (rem % 32) / D, d = rem % D;
+    return m * C + (NHU * u + hh) * D + d;
+}
 
 }  // namespace nb200

@@ -92,3 +92,31 @@ def test_swin_attn_fused(B, H, W, C, shift):
     log_metric("swin_attn_fused", B=B, H=H, W=W, C=C, shift=shift, err=err, mean=mean, vs_unfused=d2)
     assert err < 1.5e-2 and mean < 1e-3, (err, mean)
     assert d2 < 4e-3, d2
+
+
+@pytest.mark.parametrize("B,H,W,C,shift", [
+    (1, 12, 12, 192, 0), (1, 12, 12, 192, 3), (2, 18, 24, 192, 3), (1, 6, 6, 192, 3), (1, 12, 12, 96, 0), (2, 24, 18, 96, 3),
+    (3, 48, 48, 192, 3), (2, 60, 60, 96, 3), (5, 30, 30, 192, 0), (16, 60, 60, 192, 3), (7, 18, 12, 96, 3),
+])
+def test_swin_attn_tc(B, H, W, C, shift):
+    """csrc/swin_attn_tc.cu (QK^T and PV on tcgen05 as well) against the fp32 oracle on fp16 operands and against the mma.sync
+    kernel.  The shapes cover windows that wrap in x only, in y only and in both (2 / 2 / 4 TMA boxes, token order restored in
+    the epilogue), partial last tiles (windows % 3 != 0) and both head layouts (d = 32: one head per unit, d = 16: two)."""
+    g = torch.Generator(device="cpu").manual_seed(B * H + W + C + shift)
+    x = torch.randn(B, H, W, C, generator=g).half().to(DEV)
+    wqkv = (torch.randn(3 * C, C, generator=g) / C ** 0.5).half().to(DEV)
+    bqkv = (0.1 * torch.randn(3 * C, generator=g)).to(DEV)
+    table = (0.5 * torch.randn(121, 6, generator=g)).to(DEV)
+    att = torch.full((B, H, W, C), 7.0, dtype=torch.float16, device=DEV)
+    ref2 = torch.full((B, H, W, C), 7.0, dtype=torch.float16, device=DEV)
+    args = (_lib.ptr(x), _lib.ptr(wqkv), _lib.ptr(bqkv), _lib.ptr(table))
+    _lib.check(_lib.lib().nb200_swin_attn_tc_f16(*args, _lib.ptr(att), B, H, W, C, shift, _lib.stream_ptr()))
+    _lib.check(_lib.lib().nb200_swin_attn_fused_f16(*args, _lib.ptr(ref2), B, H, W, C, shift, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    want = _attn_ref(x, wqkv, bqkv, table, shift)
+    d = (att.float().cpu() - want).abs()
+    err, mean = d.max().item(), d.mean().item()
+    d2 = (att.float() - ref2.float()).abs().max().item()
+    log_metric("swin_attn_tc", B=B, H=H, W=W, C=C, shift=shift, err=err, mean=mean, vs_mma_sync=d2)
+    assert err < 1.5e-2 and mean < 1e-3, (err, mean)
+    assert d2 < 4e-3, d2
