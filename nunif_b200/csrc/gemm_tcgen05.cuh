@@ -66,7 +66,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // cold path of mbar_wait, kept out of line: the call sites of a warp-specialised kernel are many and instruction-cache space is
 // what those kernels run out of first (profiles/r2/attn_tc_ncu_v7_source.txt: most stalls of the working warps are no-instruction)
-__device__ __noinline__ void mbar_timeout() {
+static __device__ __noinline__ void mbar_timeout() {
     printf("nb200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
     __trap();
 }

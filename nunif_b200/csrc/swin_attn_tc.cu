@@ -118,7 +118,8 @@ struct WinInfo {
     int b, wy, wx;
     bool valid, xs, ys;      // xs / ys: the window wraps around the rolled image in x / y
 };
-__device__ __forceinline__ WinInfo win_info(const TcParams& p, int tile, int w) {
+// out of line: three roles decode windows once per tile; two integer divisions by run-time values are ~100 instructions inlined
+__device__ __noinline__ WinInfo win_info(const TcParams& p, int tile, int w) {
     WinInfo wi;
     const int win = tile * WPT + w;
     wi.valid = win < p.nwin;
