@@ -45,7 +45,45 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
-// explicit shared-space accesses (the carved-up dynamic buffer is a generic pointer to the compiler)
+// Everything below addresses shared memory by its 32-bit shared-space address: generic pointers cost a cvta and 64-bit
+// arithmetic at every use, and instruction-cache footprint is what this kernel runs out of first (see the header).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// try_wait in a PTX-level loop (a suspend-time hint measured no faster and triples the code of every call site).  UNBOUNDED: the protocol below is
+// validated by tests/test_gpu_fused.py::test_swin_attn_tc; build with -DNB200_TC_BOUNDED_WAITS (traps after ~5 s) when changing it.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef NB200_TC_BOUNDED_WAITS
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 18) && !done; ++it)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    if (!done) mbar_timeout();
+#else
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#endif
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// explicit shared-space accesses
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -149,32 +187,33 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
     constexpr int THREADS = Cfg::THREADS;
 
     extern __shared__ uint8_t smem_dyn[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sX = smem;                       // [KCH][128][64] 128B-swizzled; rows 108..127 stay zero
-    uint8_t* sW = smem + Cfg::OFF_W;          // weight ring
-    uint8_t* sQ = smem + Cfg::OFF_Q;          // 2 x [128][32]
-    uint8_t* sK = smem + Cfg::OFF_K;          // 2 x [112][32]
-    uint8_t* sV = smem + Cfg::OFF_V;          // 2 x NHU x V^T
-    uint8_t* sP = smem + Cfg::OFF_P;          // 2 x [2 chunks][128][64]
-    float* sBT = reinterpret_cast<float*>(smem + Cfg::OFF_BT);   // [6][121], log2(e) folded in
-    float* sBias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-    uint64_t* w_full = bars;             // [S]
-    uint64_t* w_empty = w_full + S;      // [S]
-    uint64_t* x_full = w_empty + S;
-    uint64_t* x_empty = x_full + 1;
-    uint64_t* d_full = x_empty + 1;      // [2]
-    uint64_t* d_empty = d_full + 2;      // [2]
-    uint64_t* qk_full = d_empty + 2;     // [2]
-    uint64_t* qk_empty = qk_full + 2;    // [2]
-    uint64_t* v_full = qk_empty + 2;     // [2]
-    uint64_t* v_empty = v_full + 2;      // [2]
-    uint64_t* s_full = v_empty + 2;      // [2]
-    uint64_t* s_free = s_full + 2;       // [2]
-    uint64_t* o_full = s_free + 2;       // [2]
-    uint64_t* p_full = o_full + 2;       // [2]
-    uint64_t* p_empty = p_full + 2;      // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);   // generic: prologue fills only
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t sX = sb;                        // [KCH][128][64] 128B-swizzled; rows 108..127 stay zero
+    const uint32_t sW = sb + Cfg::OFF_W;           // weight ring
+    const uint32_t sQ = sb + Cfg::OFF_Q;           // 2 x [128][32]
+    const uint32_t sK = sb + Cfg::OFF_K;           // 2 x [112][32]
+    const uint32_t sV = sb + Cfg::OFF_V;           // 2 x NHU x V^T
+    const uint32_t sP = sb + Cfg::OFF_P;           // 2 x [2 chunks][128][64]
+    const uint32_t sBT = sb + Cfg::OFF_BT;         // [6][121] fp32, log2(e) folded in
+    const uint32_t sBias = sb + Cfg::OFF_BIAS;     // [3C] fp32, packed order
+    // mbarriers (8 bytes each)
+    const uint32_t w_full = sb + Cfg::OFF_BAR;     // [S]
+    const uint32_t w_empty = w_full + 8 * S;       // [S]
+    const uint32_t x_full = w_empty + 8 * S;
+    const uint32_t x_empty = x_full + 8;
+    const uint32_t d_full = x_empty + 8;           // [2]
+    const uint32_t d_empty = d_full + 16;          // [2]
+    const uint32_t qk_full = d_empty + 16;         // [2]
+    const uint32_t qk_empty = qk_full + 16;        // [2]
+    const uint32_t v_full = qk_empty + 16;         // [2]
+    const uint32_t v_empty = v_full + 16;          // [2]
+    const uint32_t s_full = v_empty + 16;          // [2]
+    const uint32_t s_free = s_full + 16;           // [2]
+    const uint32_t o_full = s_free + 16;           // [2]
+    const uint32_t p_full = o_full + 16;           // [2]
+    const uint32_t p_empty = p_full + 16;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 * (2 * S + 2 + 22));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // debug timeline (CTA 0): tracks 0 MMA issuer, 1 E warp 8, 2 softmax warp 16, 3 softmax warp 20, 4 X producer 5, 5 W producer 0
@@ -190,13 +229,13 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.x66); tma_prefetch_desc(&maps.x36); tma_prefetch_desc(&maps.x63); tma_prefetch_desc(&maps.x33);
         tma_prefetch_desc(&maps.w);
-        for (int s = 0; s < S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init((w_full + 8 * (s)), 1); mbar_init((w_empty + 8 * (s)), 1); }
         mbar_init(x_full, WPT); mbar_init(x_empty, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 4);
-            mbar_init(&qk_full[s], 4); mbar_init(&qk_empty[s], 1); mbar_init(&v_full[s], 4); mbar_init(&v_empty[s], 1);
-            mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4); mbar_init(&o_full[s], 1);
-            mbar_init(&p_full[s], 4); mbar_init(&p_empty[s], 1);
+            mbar_init((d_full + 8 * (s)), 1); mbar_init((d_empty + 8 * (s)), 4);
+            mbar_init((qk_full + 8 * (s)), 4); mbar_init((qk_empty + 8 * (s)), 1); mbar_init((v_full + 8 * (s)), 4); mbar_init((v_empty + 8 * (s)), 1);
+            mbar_init((s_full + 8 * (s)), 1); mbar_init((s_free + 8 * (s)), 4); mbar_init((o_full + 8 * (s)), 1);
+            mbar_init((p_full + 8 * (s)), 4); mbar_init((p_empty + 8 * (s)), 1);
         }
         fence_barrier_init();
     }
@@ -204,13 +243,13 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
     if (warp == 4) tmem_alloc<512>(tmem_slot);
     // launch constants and zero fills: bias table, qkv bias; x tile (its 20 pad rows are never written again), Q / K (rows that
     // no token owns), P (everything outside the diagonal blocks), V^T (rows d+1.. and the ones row d)
-    for (int i = threadIdx.x; i < BT_FLOATS; i += THREADS) sBT[i] = LOG2E * __ldg(p.bias_tab + (i % RT) * HEADS + i / RT);
-    for (int i = threadIdx.x; i < 3 * C; i += THREADS) sBias[i] = __ldg(p.bqkv + i);
-    for (int i = threadIdx.x; i < Cfg::XB / 16; i += THREADS) reinterpret_cast<uint4*>(sX)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < (Cfg::OFF_BT - Cfg::OFF_Q) / 16; i += THREADS) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < BT_FLOATS; i += THREADS) reinterpret_cast<float*>(smem + Cfg::OFF_BT)[i] = LOG2E * __ldg(p.bias_tab + (i % RT) * HEADS + i / RT);
+    for (int i = threadIdx.x; i < 3 * C; i += THREADS) reinterpret_cast<float*>(smem + Cfg::OFF_BIAS)[i] = __ldg(p.bqkv + i);
+    for (int i = threadIdx.x; i < Cfg::XB / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (Cfg::OFF_BT - Cfg::OFF_Q) / 16; i += THREADS) reinterpret_cast<uint4*>(smem + Cfg::OFF_Q)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * NHU * 2 * 8; i += THREADS)     // ones row: 8 x 16 B per chunk (the swizzle permutes 16 B units inside a row)
-        reinterpret_cast<uint4*>(sV + (i >> 3) * Cfg::VCH + D * 128)[i & 7] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+        reinterpret_cast<uint4*>(smem + Cfg::OFF_V + (i >> 3) * Cfg::VCH + D * 128)[i & 7] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
     fence_async_smem();     // the fills are read by the tensor core through the async proxy
     tc_fence_before();
     __syncthreads();
@@ -227,10 +266,10 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             for (int gs = warp; gs < nst; gs += 2) {
                 const int gu = gs / KCH, kc = gs - gu * KCH, u = gu % UPT, ws = gs % S;
                 if (warp == 0) TTL(5, 50, u);
-                mbar_wait(&w_empty[ws], ((gs / S) & 1) ^ 1);
+                mbar_wait((w_empty + 8 * (ws)), ((gs / S) & 1) ^ 1);
                 if (warp == 0) TTL(5, 51, u);
-                mbar_expect_tx(&w_full[ws], WST);
-                tma_load_2d(&maps.w, &w_full[ws], sW + ws * WST, kc * 64, u * UN);
+                mbar_expect_tx((w_full + 8 * (ws)), WST);
+                tma_load_2d(&maps.w, (w_full + 8 * (ws)), sW + ws * WST, kc * 64, u * UN);
             }
         }
     } else if (warp == 2) {
@@ -240,15 +279,16 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
         // at the ~19 cycles per instruction a warp of this kernel gets (ncu: 17 % no-instruction, 40 % scoreboard) that is one issued
         // item per ~1000 cycles - every hand-off of the pipeline waited on the issuer.)
         const uint32_t idesc_g = make_idesc_f16(UN);
-        const uint32_t aX = smem_u32(sX), aW = smem_u32(sW);
+        const uint32_t aX = sX, aW = sW;
         int gstage = 0;
         for (int gu = 0; gu < total_units; ++gu) {
             const int b = gu & 1, u = gu % UPT;
-            mbar_wait(&d_empty[b], ((gu >> 1) & 1) ^ 1);
+            mbar_wait((d_empty + 8 * (b)), ((gu >> 1) & 1) ^ 1);
             if (u == 0) mbar_wait(x_full, (gu / UPT) & 1);
+#pragma unroll 1
             for (int kc = 0; kc < KCH; ++kc, ++gstage) {
                 const int ws = gstage % S;
-                mbar_wait(&w_full[ws], (gstage / S) & 1);
+                mbar_wait((w_full + 8 * (ws)), (gstage / S) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t td = tmem_base + Cfg::TM_D + b * UN;
@@ -257,9 +297,9 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                     for (int k = 0; k < ksteps; ++k)
                         umma_f16(td, make_kmajor_desc<128>(aX + kc * XCH + k * 32), make_kmajor_desc<128>(aW + ws * WST + k * 32), idesc_g,
                                  (kc > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&w_empty[ws]);
+                    umma_commit((w_empty + 8 * (ws)));
                     if (kc == KCH - 1) {
-                        umma_commit(&d_full[b]);
+                        umma_commit((d_full + 8 * (b)));
                         if (u == UPT - 1) umma_commit(x_empty);   // the activation tile may be overwritten
                     }
                 }
@@ -269,11 +309,11 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
     } else if (warp == 3) {
         // ===================== S issuer: S[h & 1] = Qh . Kh^T =====================
         const uint32_t idesc_s = make_idesc_f16(SN);
-        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+        const uint32_t aQ = sQ, aK = sK;
         for (int h = 0; h < total_heads; ++h) {
             const int gu = h / NHU, hh = h - gu * NHU, b = gu & 1, sl = h & 1;
-            if (hh == 0) mbar_wait(&qk_full[b], (gu >> 1) & 1);
-            mbar_wait(&s_free[sl], ((h >> 1) & 1) ^ 1);
+            if (hh == 0) mbar_wait((qk_full + 8 * (b)), (gu >> 1) & 1);
+            mbar_wait((s_free + 8 * (sl)), ((h >> 1) & 1) ^ 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t td = tmem_base + Cfg::TM_S + sl * Cfg::TM_SSTRIDE;
@@ -281,19 +321,19 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                 for (int k = 0; k < D / 16; ++k)
                     umma_f16(td, make_kmajor_desc<64>(aQ + b * Cfg::QB + hh * 2 * D + k * 32), make_kmajor_desc<64>(aK + b * Cfg::KB + hh * 2 * D + k * 32),
                              idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(&s_full[sl]);
-                if (hh == NHU - 1) umma_commit(&qk_empty[b]);
+                umma_commit((s_full + 8 * (sl)));
+                if (hh == NHU - 1) umma_commit((qk_empty + 8 * (b)));
             }
             __syncwarp();
         }
     } else if (warp == 4) {
         // ===================== PV issuer: O[h & 1] = P[h & 1] . Vh (K = 112: tokens 0..111) =====================
         const uint32_t idesc_o = make_idesc_f16(NV);
-        const uint32_t aV = smem_u32(sV), aP = smem_u32(sP);
+        const uint32_t aV = sV, aP = sP;
         for (int h = 0; h < total_heads; ++h) {
             const int gu = h / NHU, hh = h - gu * NHU, b = gu & 1, sl = h & 1;
-            if (hh == 0) mbar_wait(&v_full[b], (gu >> 1) & 1);
-            mbar_wait(&p_full[sl], (h >> 1) & 1);
+            if (hh == 0) mbar_wait((v_full + 8 * (b)), (gu >> 1) & 1);
+            mbar_wait((p_full + 8 * (sl)), (h >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t td = tmem_base + Cfg::TM_S + sl * Cfg::TM_SSTRIDE + Cfg::TM_O;
@@ -305,9 +345,9 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                     umma_f16(td, make_kmajor_desc<128>(ap + kc2 * Cfg::PCH + kk * 32), make_kmajor_desc<128>(av + kc2 * Cfg::VCH + kk * 32), idesc_o,
                              k > 0 ? 1u : 0u);
                 }
-                umma_commit(&o_full[sl]);
-                umma_commit(&p_empty[sl]);
-                if (hh == NHU - 1) umma_commit(&v_empty[b]);
+                umma_commit((o_full + 8 * (sl)));
+                umma_commit((p_empty + 8 * (sl)));
+                if (hh == NHU - 1) umma_commit((v_empty + 8 * (b)));
             }
             __syncwarp();
         }
@@ -325,10 +365,10 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                 if (!wi.valid) { mbar_arrive(x_full); continue; }
                 mbar_expect_tx(x_full, (uint32_t)(WTOK * 128 * KCH));
                 const int y0 = wi.wy * WS + p.shift, x0 = wi.wx * WS + p.shift;   // torch.roll(-shift): window row r <- row (r + shift) % H
-                uint8_t* dst = sX + j * WTOK * 128;
+                const uint32_t dst = sX + j * WTOK * 128;
 #pragma unroll 1
                 for (int kc = 0; kc < KCH; ++kc) {
-                    uint8_t* d = dst + kc * XCH;
+                    const uint32_t d = dst + kc * XCH;
                     if (!wi.xs && !wi.ys) {
                         tma_load_4d(&maps.x66, x_full, d, kc * 64, x0, y0, wi.b);
                     } else if (!wi.xs) {          // two boxes of 3 whole window rows
@@ -353,7 +393,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
         const int w = r < 36 ? 0 : (r < 72 ? 1 : 2);
         const int l = r - 36 * w;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::TM_D + b * UN;
-        const uint32_t qb = smem_u32(sQ + b * Cfg::QB), kb = smem_u32(sK + b * Cfg::KB), vb = smem_u32(sV + b * NHU * Cfg::VTB);
+        const uint32_t qb = sQ + b * Cfg::QB, kb = sK + b * Cfg::KB, vb = sV + b * NHU * Cfg::VTB;
         int cur_ti = -1;
         bool rv = false;
         uint32_t qoff[4] = {0, 0, 0, 0};     // byte offset of the four 16-byte pieces of row R in a 64B-swizzled [rows][32] operand
@@ -374,10 +414,10 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             }
             const bool tle = warp == 8 && lane == 0;
             if (tle) TTL(1, 10, u);
-            mbar_wait(&d_full[b], (gu >> 1) & 1);
+            mbar_wait((d_full + 8 * (b)), (gu >> 1) & 1);
             tc_fence_after();
             if (tle) TTL(1, 11, u);
-            const uint32_t bia = smem_u32(sBias + u * UN);
+            const uint32_t bia = sBias + 4 * (u * UN);
             const uint32_t par_e = ((gu >> 1) & 1) ^ 1;
             // ---- q and k: 32 columns each -> one 64-byte row of the 64B-swizzled operand
 #pragma unroll 1
@@ -387,7 +427,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                 tmem_ld16(tlane + m * 32 + 16, acc[1]);
                 tmem_ld_wait();
                 if (tle) TTL(1, 14, m);
-                if (m == 0) mbar_wait(&qk_empty[b], par_e);
+                if (m == 0) mbar_wait((qk_empty + 8 * (b)), par_e);
                 if (rv) {
                     const uint32_t base = m == 0 ? qb : kb;
 #pragma unroll
@@ -406,7 +446,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             if (tle) TTL(1, 15, u);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&qk_full[b]);
+            if (lane == 0) mbar_arrive((qk_full + 8 * (b)));
             if (tle) TTL(1, 12, u);
             // ---- v: transposed, V^T[head][dd][token R]
             {
@@ -416,9 +456,9 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[b]);       // every column of D has been pulled by this warp
+                if (lane == 0) mbar_arrive((d_empty + 8 * (b)));       // every column of D has been pulled by this warp
                 if (tle) TTL(1, 16, u);
-                mbar_wait(&v_empty[b], par_e);
+                mbar_wait((v_empty + 8 * (b)), par_e);
                 if (tle) TTL(1, 17, u);
                 if (rv) {
 #pragma unroll
@@ -437,7 +477,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             if (tle) TTL(1, 18, u);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&v_full[b]);
+            if (lane == 0) mbar_arrive((v_full + 8 * (b)));
             if (tle) TTL(1, 13, u);
         }
     } else {
@@ -455,7 +495,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
 #pragma unroll
         for (int m = 0; m < 9; ++m) {
             const int cb = 72 * w + 8 * m, within = cb & 127;   // byte column of P
-            paddr[m] = smem_u32(sP + kk * Cfg::PB + r * 128) + (cb >> 7) * Cfg::PCH + ((((within >> 4) ^ (r & 7))) << 4) + (within & 15);
+            paddr[m] = sP + kk * Cfg::PB + r * 128 + (cb >> 7) * Cfg::PCH + ((((within >> 4) ^ (r & 7))) << 4) + (within & 15);
         }
         const int rbase = (yq + WS - 1) * (2 * WS - 1) + xq + WS - 1;   // relative position index of key (0, 0)
         int cur_ti = -1;
@@ -469,7 +509,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
         const bool tls = q == 0 && lane == 0;
         const int ttr = 2 + kk;
         auto o_epilogue = [&]() {
-            mbar_wait(&o_full[kk], o_par);
+            mbar_wait((o_full + 8 * (kk)), o_par);
             tc_fence_after();
             if (tls) TTL(ttr, 28, 0);
             uint32_t o[D], os[4];
@@ -515,7 +555,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
                 tok = ((size_t)wi.b * p.H + y) * p.W + x;
             }
             if (tls) TTL(ttr, 20, hd);
-            mbar_wait(&s_full[kk], (gh >> 1) & 1);
+            mbar_wait((s_full + 8 * (kk)), (gh >> 1) & 1);
             tc_fence_after();
             if (tls) TTL(ttr, 21, hd);
             // ---- the 36 columns of this row's window (36 w ..): warps that straddle two windows read both and select
@@ -536,10 +576,10 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[kk]);     // S(h + 2) may overwrite the S columns (O has its own)
+            if (lane == 0) mbar_arrive((s_free + 8 * (kk)));     // S(h + 2) may overwrite the S columns (O has its own)
             if (tls) TTL(ttr, 22, hd);
             float s[WTOK];
-            const uint32_t bt = smem_u32(sBT + hd * RT + rbase);
+            const uint32_t bt = sBT + 4 * (hd * RT + rbase);
 #pragma unroll
             for (int c = 0; c < WTOK; ++c) s[c] = fmaf(__uint_as_float(sa[c]), scale, lds32(bt - 4 * ((c / WS) * (2 * WS - 1) + (c % WS))));
             if (anyb) {
@@ -556,7 +596,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             if (o_pending) o_epilogue();                 // head gh - 2: its PV has had a whole softmax to finish
             if (!live) break;
             if (tls) TTL(ttr, 24, hd);
-            mbar_wait(&p_empty[kk], ((gh >> 1) & 1) ^ 1);
+            mbar_wait((p_empty + 8 * (kk)), ((gh >> 1) & 1) ^ 1);
             if (tls) TTL(ttr, 26, hd);
             if (rv) {
 #pragma unroll
@@ -565,7 +605,7 @@ __global__ void __launch_bounds__(TcCfg<C>::THREADS, 1) swin_attn_tc_kernel(cons
             if (tls) TTL(ttr, 27, hd);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[kk]);
+            if (lane == 0) mbar_arrive((p_full + 8 * (kk)));
             if (tls) TTL(ttr, 25, hd);
             o_pending = true; o_rv = rv; o_dst = p.att + tok * C + hd * D; o_par = (gh >> 1) & 1;
         }
