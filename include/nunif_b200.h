@@ -85,7 +85,8 @@ enum {
     NB200_MODEL_DEPTH_ANYTHING_V2_S = 6,
     NB200_MODEL_ROW_FLOW_V3 = 7,    /* sbs.row_flow_v3, iw3's default learned stereo warp (iw3/models/row_flow_v3.py) */
     NB200_MODEL_DEPTH_ANYTHING_V2_B = 8,   /* Any_V2_B: ViT-B encoder, 128 head features */
-    NB200_MODEL_DEPTH_ANYTHING_V2_L = 9    /* Any_V2_L: ViT-L encoder (24 blocks), 256 head features */
+    NB200_MODEL_DEPTH_ANYTHING_V2_L = 9,   /* Any_V2_L: ViT-L encoder (24 blocks), 256 head features */
+    NB200_MODEL_DEPTH_AA = 10              /* iw3.depth_aa, learned anti-aliasing of the depth map (iw3/models/depth_aa.py) */
 };
 
 /* Create a model from named fp32 host tensors using the reference's state_dict
@@ -130,6 +131,11 @@ int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, i
  * -> depth [B][H][W] fp32 (relative inverse depth, larger = nearer). */
 int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth,
                                  void* stream);
+
+/* iw3.depth_aa (iw3/models/depth_aa.py:46-87; applied by batch_infer when depth_aa is set, iw3/depth_anything_model.py:153-154):
+ * x [B][1][H][W] fp32 -> out, same shape.  mode 0 = forward in eval mode (clamp to [0,1]), 1 = infer (normalise by the
+ * min / max of the WHOLE tensor, filter without clamp, de-normalise), 2 = forward(clamp=False). */
+int nb200_depth_aa(nb200_model* m, const float* x, int B, int H, int W, int mode, float* out, void* stream);
 
 /* sbs.row_flow_v3 in delta_output mode (iw3/models/row_flow_v3.py:57-68,111-116): x [B][3][h][w] fp32 = depth,
  * divergence feature, convergence feature (make_input_tensor, iw3/backward_warp.py:18-63) -> delta [B][1][h][w]

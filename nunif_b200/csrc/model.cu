@@ -8,6 +8,7 @@
 #include "cunet_kernels.h"
 #include "depth_kernels.h"
 #include "rowflow_kernels.h"
+#include "depth_aa_kernels.h"
 #include "swin_fused.h"
 #include "../../include/nunif_b200.h"
 #include <map>
@@ -206,6 +207,7 @@ struct SwinW {
 struct CUNetW;  // cunet_model.inl
 struct DaW;     // depth_model.inl
 struct RfW;     // rowflow_model.inl
+struct AaW;     // depth_aa_model.inl
 
 }  // namespace nb200
 
@@ -220,6 +222,7 @@ struct nb200_model {
     std::shared_ptr<CUNetW> cu;
     std::shared_ptr<DaW> da;
     std::shared_ptr<RfW> rf;
+    std::shared_ptr<AaW> aa;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
@@ -553,6 +556,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 #include "cunet_model.inl"
 #include "depth_model.inl"
 #include "rowflow_model.inl"
+#include "depth_aa_model.inl"
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -560,7 +564,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
                                   const int64_t* numel, int no_clip, nb200_model** out) {
     NB_CHECK(out && names && data && numel, "null pointer");
-    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_DEPTH_ANYTHING_V2_L, "unknown model kind");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_DEPTH_AA, "unknown model kind");
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
@@ -588,6 +592,7 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
         case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk, 0); m->scale = 1; break;
         case NB200_MODEL_DEPTH_ANYTHING_V2_B: m->da = pack_depth_anything(pk, 1); m->scale = 1; break;
         case NB200_MODEL_DEPTH_ANYTHING_V2_L: m->da = pack_depth_anything(pk, 2); m->scale = 1; break;
+        case NB200_MODEL_DEPTH_AA: m->aa = pack_depth_aa(pk); m->scale = 1; break;                                     // depth_aa.py:34
         case NB200_MODEL_ROW_FLOW_V3: m->rf = pack_row_flow(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;   // row_flow_v3.py:37
     }
     if (pk.err.empty())
@@ -802,6 +807,14 @@ extern "C" int nb200_depth_anything_forward(nb200_model* m, const float* x, int 
     NB_CHECK(m->da, "model is not a Depth-Anything network");
     NB_CHECK(B > 0, "empty batch");
     return depth_anything_forward(m, (cudaStream_t)stream, x, B, H, W, depth);
+}
+
+// DepthAA.forward / DepthAA.infer (iw3/models/depth_aa.py:46-87)
+extern "C" int nb200_depth_aa(nb200_model* m, const float* x, int B, int H, int W, int mode, float* out, void* stream) {
+    NB_CHECK(m && x && out, "null pointer");
+    NB_CHECK(m->kind == NB200_MODEL_DEPTH_AA && m->aa, "model is not iw3.depth_aa");
+    NB_CHECK(B > 0 && H > 0 && W > 0 && mode >= 0 && mode <= 2, "bad arguments");
+    return depth_aa_forward(m, (cudaStream_t)stream, x, B, H, W, mode, out);
 }
 
 // RowFlowV3.forward with delta_output=True (iw3/models/row_flow_v3.py:111-116) - the x component of the returned delta

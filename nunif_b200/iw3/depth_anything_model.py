@@ -65,18 +65,18 @@ class DepthAnythingNet:
 def batch_infer(model, im, flip_aug=True, low_vram=False, enable_amp=False, output_device="cpu", device=None,
                 edge_dilation=2, depth_aa=None, limit_resolution=False, **kwargs):
     """depth_anything_model.py:122-182.  ``enable_amp`` is accepted for signature parity: the engine always runs the
-    reference's CUDA numerics (fp16 autocast).  ``depth_aa`` (a learned post-filter, iw3/models/depth_aa.py) is not part
-    of the B200 path."""
+    reference's CUDA numerics (fp16 autocast).  ``depth_aa``: a packed `iw3.depth_aa` (nunif_b200.iw3.depth_aa.DepthAA) or
+    None (:153-154)."""
     device = device if device is not None else model.device
     assert torch.is_tensor(im) and im.ndim in (3, 4)
     batch = im.ndim == 4
     x = (im if batch else im.unsqueeze(0)).to(device)
-    if depth_aa is not None:
-        raise NotImplementedError("depth_aa is not implemented by the B200 engine")
     x = batch_preprocess(x, model.prep_lower_bound, limit_resolution=limit_resolution)
     if flip_aug:
         x = torch.cat([x, torch.flip(x, dims=[3])], dim=0)           # :140-142 (low_vram only changes the batching)
     out = torch.nan_to_num(model(x).unsqueeze(1))                    # _forward :113-119
+    if depth_aa is not None:
+        out = depth_aa.infer(out)                                    # :153-154
     if edge_dilation_is_enabled(edge_dilation):
         out = dilate_edge(out, edge_dilation) if not model.metric_depth else -dilate_edge(-out, edge_dilation)
     if model.metric_depth:
@@ -153,8 +153,18 @@ class DepthAnythingModel(BaseDepthModel):
             import numpy as np
             x = torch.from_numpy(np.asarray(x, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0).to(self.device)
         _lib.require_cuda(x, "x")
-        if depth_aa:
-            raise NotImplementedError("depth_aa is not implemented by the B200 engine")
+        if depth_aa and getattr(self, "depth_aa", None) is None:
+            raise RuntimeError("depth_aa=True needs the iw3.depth_aa weights: call load_depth_aa(state_dict) first (the reference "
+                               "downloads iw3_depth_aa_20250530.pth in load(), :190-192; nunif_b200 does not download)")
         return batch_infer(self.model, x, flip_aug=tta, low_vram=low_vram, enable_amp=enable_amp, output_device=x.device,
-                           device=x.device, edge_dilation=edge_dilation, depth_aa=None,
+                           device=x.device, edge_dilation=edge_dilation, depth_aa=self.depth_aa if depth_aa else None,
                            limit_resolution=self.limit_resolution)
+
+    depth_aa = None
+
+    def load_depth_aa(self, state_dict):
+        """The learned anti-aliasing filter the reference attaches in load() (:190-194); ``state_dict`` with the keys of
+        `iw3.depth_aa` (the ``state_dict`` entry of iw3_depth_aa_20250530.pth)."""
+        from .depth_aa import DepthAA
+        self.depth_aa = DepthAA(state_dict, self.device)
+        return self
