@@ -2,8 +2,8 @@
 its driver apply_divergence_nn_LR / apply_divergence_nn_delta (iw3/backward_warp.py:124-232).
 
 The delta network runs as tcgen05 GEMMs + the kernels in csrc/rowflow_kernels.cu; the warp is the fused grid-sample kernel
-(csrc/warp_backward.cu, nb200_backward_warp_delta).  steps > 1 (iterative re-warping of the depth) and
-preserve_screen_border are not implemented and raise NotImplementedError.
+(csrc/warp_backward.cu, nb200_backward_warp_delta).  steps > 1 (iterative re-warping of the depth, :205-226) and
+preserve_screen_border (:33-47) run the same kernels once per step.
 """
 import ctypes
 import torch
@@ -72,22 +72,46 @@ def _warp_delta(c, delta, delta_scale):
     return out
 
 
-def apply_divergence_nn_delta(model, c, depth, divergence, convergence, steps, shift, preserve_screen_border=False, enable_amp=True):
-    """iw3/backward_warp.py:185-232 (steps == 1)."""
-    if steps not in (None, 1):
-        raise NotImplementedError("steps > 1 is not implemented by the B200 engine")
+def make_input(depth, divergence, convergence, preserve_screen_border=False):
+    """make_input_tensor(None, depth, ...) for a batch (iw3/backward_warp.py:18-63): depth, divergence feature, convergence
+    feature; with preserve_screen_border the two features fade linearly to zero over `border_pix` columns at both edges."""
+    B, _, H, W = depth.shape
+    base = max(H, W)
+    dv, cv = make_divergence_feature_value(divergence, convergence, base)
+    df, cf = torch.full_like(depth, dv), torch.full_like(depth, cv)
     if preserve_screen_border:
-        raise NotImplementedError("preserve_screen_border is not implemented by the B200 engine")
+        bp = round(divergence * 0.75 * 0.01 * base * (W / base))                               # :36
+        if bp > 0:
+            wl = torch.linspace(0.0, 1.0, bp, device=depth.device)
+            wr = torch.linspace(1.0, 0.0, bp, device=depth.device)
+            for f in (df, cf):
+                f[..., :bp] = wl * f[..., :bp]
+                f[..., -bp:] = wr * f[..., -bp:]
+    return torch.cat([depth, df, cf], dim=1)
+
+
+def apply_divergence_nn_delta(model, c, depth, divergence, convergence, steps, shift, preserve_screen_border=False, enable_amp=True):
+    """iw3/backward_warp.py:185-232."""
+    steps = 1 if steps is None else int(steps)
+    assert steps >= 1
+    if not enable_amp:
+        raise NotImplementedError("nunif_b200 implements the reference's CUDA autocast (fp16) forward only")
     _lib.require_cuda(c, "c")
     _lib.require_cuda(depth, "depth")
     c, depth = c.float().contiguous(), depth.float().contiguous()
     if shift > 0:
         c, depth = torch.flip(c, (3,)), torch.flip(depth, (3,))
     B, _, H, W = depth.shape
-    dv, cv = make_divergence_feature_value(divergence, convergence, max(H, W))
-    x = torch.cat([depth, torch.full_like(depth, dv), torch.full_like(depth, cv)], dim=1)      # make_input_tensor(None, ...)
-    delta = model.delta_x(x)
-    z = _warp_delta(c, delta, 1.0 / (W // 2 - 1))                                              # :201
+    delta_scale = 1.0 / (W // 2 - 1)                                                           # :201
+    depth_warp, deltas = depth, []
+    for j in range(steps):
+        deltas.append(model.delta_x(make_input(depth_warp, divergence / steps, convergence, preserve_screen_border)))
+        if j + 1 < steps:
+            # backward_warp(depth_warp, grid, delta, delta_scale) :220-221 (the warp kernel takes 3-channel frames)
+            depth_warp = _warp_delta(depth_warp.expand(-1, 3, -1, -1).contiguous(), deltas[-1], delta_scale)[:, :1].contiguous()
+    z = c
+    for delta in deltas:                                                                       # :223-226
+        z = _warp_delta(z, delta, delta_scale)
     return torch.flip(z, (3,)) if shift > 0 else z
 
 

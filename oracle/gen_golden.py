@@ -266,6 +266,25 @@ def gen_row_flow():
     save("row_flow", **out)
 
 
+def gen_row_flow_steps():
+    """apply_divergence_nn_LR with steps > 1 (iterative re-warping of the depth, iw3/backward_warp.py:205-226) and with
+    preserve_screen_border (make_input_tensor, :33-47) through the REAL sbs.row_flow_v3."""
+    from nunif.models import create_model
+    import iw3.models  # noqa: F401  (registers sbs.*)
+    from iw3.backward_warp import apply_divergence_nn_LR
+    m = create_model("sbs.row_flow_v3").eval()
+    m.load_state_dict(synth.row_flow_v3_state_dict(0), strict=True)
+    m.delta_output = True
+    d = synth.synth_depth(3, 2, 70, 130)
+    c = torch.stack([synth.synth_image(4 + i, 3, 140, 260) for i in range(2)])
+    out = {"d": d, "c": c}
+    out["s2_left"], out["s2_right"] = apply_divergence_nn_LR(m, c, d, 2.0, 0.5, steps=2, enable_amp=False)
+    out["s3b_left"], out["s3b_right"] = apply_divergence_nn_LR(m, c, d, 4.0, 0.4, steps=3, preserve_screen_border=True, enable_amp=False)
+    out["b_left"], out["b_right"] = apply_divergence_nn_LR(m, c, d, 5.0, 0.5, steps=1, synthetic_view="left", preserve_screen_border=True,
+                                                            enable_amp=False)
+    save("row_flow_steps", **out)
+
+
 POSTPROCESS_CASES = [
     ("sbs", {}),
     ("half_sbs", {"half_sbs": True}),
@@ -358,7 +377,7 @@ def gen_mlbw():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "postprocess", "depth_scaler", "depth_aa", "mlbw"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "row_flow_steps", "postprocess", "depth_scaler", "depth_aa", "mlbw"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -371,6 +390,8 @@ if __name__ == "__main__":
         gen_frames()
     if "row_flow" in which:
         gen_row_flow()
+    if "row_flow_steps" in which:
+        gen_row_flow_steps()
     if "postprocess" in which:
         gen_postprocess()
     if "depth_scaler" in which:

@@ -1,6 +1,7 @@
 """ORACLE (test infrastructure only - never imported by nunif_b200/): CPU/torch restatement of the learned stereo
 warp `sbs.row_flow_v3` (iw3/models/row_flow_v3.py:14-128) and of its driver apply_divergence_nn_LR /
-apply_divergence_nn_delta (iw3/backward_warp.py:124-232) for steps=1, preserve_screen_border=False.
+apply_divergence_nn_delta (iw3/backward_warp.py:124-232) incl. steps > 1 and preserve_screen_border
+(tests/golden/row_flow_steps.npz).
 
 Pinned against the real reference model (create_model("sbs.row_flow_v3") with a seeded state_dict, run from
 /root/reference): tests/golden/row_flow.npz (oracle/gen_golden.py row_flow).  Functional style (state_dict in).
@@ -59,11 +60,20 @@ def row_flow_delta(sd, x):
     return F.conv2d(x, sd["last_layer.1.weight"], sd["last_layer.1.bias"])
 
 
-def make_input(depth, divergence, convergence):
+def make_input(depth, divergence, convergence, preserve_screen_border=False):
     """make_input_tensor(None, depth, ...) for a batch (backward_warp.py:8-63), image_width = max(H, W)."""
     B, _, H, W = depth.shape
-    div_pix = divergence * 0.5 * 0.01 * max(H, W)
-    return torch.cat([depth, torch.full_like(depth, div_pix / 32.0), torch.full_like(depth, (-div_pix * convergence) / 32.0)], dim=1)
+    base = max(H, W)
+    div_pix = divergence * 0.5 * 0.01 * base
+    df, cf = torch.full_like(depth, div_pix / 32.0), torch.full_like(depth, (-div_pix * convergence) / 32.0)
+    if preserve_screen_border:                               # :33-47: the parallax fades to zero towards the left / right edges
+        bp = round(divergence * 0.75 * 0.01 * base * (W / base))
+        if bp > 0:
+            wl, wr = torch.linspace(0.0, 1.0, bp), torch.linspace(1.0, 0.0, bp)
+            for f in (df, cf):
+                f[..., :bp] = wl * f[..., :bp]
+                f[..., -bp:] = wr * f[..., -bp:]
+    return torch.cat([depth, df, cf], dim=1)
 
 
 def warp_delta(c, delta, W_depth):
@@ -79,12 +89,21 @@ def warp_delta(c, delta, W_depth):
     return z.clamp(0, 1)
 
 
-def apply_divergence_nn_LR(sd, c, depth, divergence, convergence, synthetic_view="both"):
-    """backward_warp.py:124-232 for steps=1: the right eye is the left-eye procedure on the mirrored frame."""
+def apply_divergence_nn_LR(sd, c, depth, divergence, convergence, synthetic_view="both", steps=1, preserve_screen_border=False):
+    """backward_warp.py:124-232: the right eye is the left-eye procedure on the mirrored frame; with steps > 1 the divergence is
+    applied in `steps` equal parts, the DEPTH being re-warped by each part's delta before the next (:205-221), and the image is
+    warped by the deltas one after the other (:223-226)."""
     def one(shift, div):
         cc, dd = (torch.flip(c, (3,)), torch.flip(depth, (3,))) if shift > 0 else (c, depth)
-        delta = row_flow_delta(sd, make_input(dd, div, convergence))
-        z = warp_delta(cc, delta, dd.shape[3])
+        Wd = dd.shape[3]
+        dw, deltas = dd, []
+        for j in range(steps):
+            deltas.append(row_flow_delta(sd, make_input(dw, div / steps, convergence, preserve_screen_border)))
+            if j + 1 < steps:
+                dw = warp_delta(dw, deltas[-1], Wd)
+        z = cc
+        for delta in deltas:
+            z = warp_delta(z, delta, Wd)
         return torch.flip(z, (3,)) if shift > 0 else z
     if synthetic_view == "both":
         return one(-1, divergence), one(1, divergence)

@@ -88,3 +88,22 @@ def test_row_flow_1080p_runs_and_matches_oracle_amp():
     sl, sr = stats(l, lo), stats(r, ro)
     log_metric("row_flow_1080p", left_max=sl["max"], right_max=sr["max"], left_mean=sl["mean"], right_mean=sr["mean"])
     assert sl["mean"] < 1e-3 and sr["mean"] < 1e-3
+
+
+@pytest.mark.parametrize("lk,rk,div,conv,sv,steps,border", [
+    ("s2_left", "s2_right", 2.0, 0.5, "both", 2, False), ("s3b_left", "s3b_right", 4.0, 0.4, "both", 3, True),
+    ("b_left", "b_right", 5.0, 0.5, "left", 1, True)])
+def test_apply_divergence_nn_LR_steps_and_border_golden(lk, rk, div, conv, sv, steps, border):
+    """steps > 1 (the depth is re-warped by each step's delta, iw3/backward_warp.py:205-226) and preserve_screen_border
+    (:33-47) against the REAL reference model's fp32 CPU output (tests/golden/row_flow_steps.npz)."""
+    from nunif_b200.iw3 import RowFlowV3, apply_divergence_nn_LR
+    g = load_golden("row_flow_steps")
+    m = RowFlowV3(synth.row_flow_v3_state_dict(0), DEV)
+    c, d = t(g["c"], DEV), t(g["d"], DEV)
+    l, r = apply_divergence_nn_LR(m, c, d, div, conv, steps=steps, synthetic_view=sv, preserve_screen_border=border)
+    sl, sr = stats(l, t(g[lk])), stats(r, t(g[rk]))
+    log_metric(f"row_flow_steps{steps}_border{int(border)}", left_max=sl["max"], right_max=sr["max"], left_mean=sl["mean"], right_mean=sr["mean"])
+    # same bound as the single-step test: fp16 delta network against the reference's fp32 run, errors accumulate over the steps
+    assert sl["mean"] < 1e-3 * steps and sr["mean"] < 1e-3 * steps and sl["max"] < 3e-2 * steps and sr["max"] < 3e-2 * steps, (sl, sr)
+    if sv == "left":
+        assert torch.equal(r, c)

@@ -301,6 +301,21 @@ def test_row_flow_oracle_matches_reference():
         assert float((l - t(g["left2"])).abs().max()) < 1e-5 and float((r - t(g["right2"])).abs().max()) < 1e-5
 
 
+def test_row_flow_steps_oracle_matches_reference():
+    """steps > 1 and preserve_screen_border of apply_divergence_nn_LR, pinned against the real reference model."""
+    from oracle import row_flow as orf
+    g = load_golden("row_flow_steps")
+    sd = synth.row_flow_v3_state_dict(0)
+    c, d = t(g["c"]), t(g["d"])
+    with torch.no_grad():
+        l, r = orf.apply_divergence_nn_LR(sd, c, d, 2.0, 0.5, steps=2)
+        assert float((l - t(g["s2_left"])).abs().max()) < 1e-5 and float((r - t(g["s2_right"])).abs().max()) < 1e-5
+        l, r = orf.apply_divergence_nn_LR(sd, c, d, 4.0, 0.4, steps=3, preserve_screen_border=True)
+        assert float((l - t(g["s3b_left"])).abs().max()) < 1e-5 and float((r - t(g["s3b_right"])).abs().max()) < 1e-5
+        l, r = orf.apply_divergence_nn_LR(sd, c, d, 5.0, 0.5, "left", preserve_screen_border=True)
+        assert float((l - t(g["b_left"])).abs().max()) < 1e-5 and torch.equal(r, t(g["b_right"]))
+
+
 def _pp_kwargs(kw):
     kw = dict(kw)
     if "anaglyph" in kw:
