@@ -86,7 +86,8 @@ enum {
     NB200_MODEL_ROW_FLOW_V3 = 7,    /* sbs.row_flow_v3, iw3's default learned stereo warp (iw3/models/row_flow_v3.py) */
     NB200_MODEL_DEPTH_ANYTHING_V2_B = 8,   /* Any_V2_B: ViT-B encoder, 128 head features */
     NB200_MODEL_DEPTH_ANYTHING_V2_L = 9,   /* Any_V2_L: ViT-L encoder (24 blocks), 256 head features */
-    NB200_MODEL_DEPTH_AA = 10              /* iw3.depth_aa, learned anti-aliasing of the depth map (iw3/models/depth_aa.py) */
+    NB200_MODEL_DEPTH_AA = 10,             /* iw3.depth_aa, learned anti-aliasing of the depth map (iw3/models/depth_aa.py) */
+    NB200_MODEL_MLBW = 11                  /* sbs.mlbw, multi-layer learned stereo warp, num_layers 2 | 4 (iw3/models/mlbw.py) */
 };
 
 /* Create a model from named fp32 host tensors using the reference's state_dict
@@ -141,6 +142,12 @@ int nb200_depth_aa(nb200_model* m, const float* x, int B, int H, int W, int mode
  * divergence feature, convergence feature (make_input_tensor, iw3/backward_warp.py:18-63) -> delta [B][1][h][w]
  * fp32 (the x component; the y component is zero). */
 int nb200_row_flow_delta(nb200_model* m, const float* x, int B, int h, int w, float* delta, void* stream);
+
+/* sbs.mlbw in delta_output mode (iw3/models/mlbw.py:96-127,237-245): x [B][3][h][w] fp32 (depth, divergence feature,
+ * convergence feature) -> delta [B][L][h][w] (x component of each flow layer) and layer_weight [B][L][h][w] (softmax over
+ * the L layers); L = nb200_mlbw_num_layers (2 or 4, read off the state_dict).  hole_mask models are not supported. */
+int nb200_mlbw_delta(nb200_model* m, const float* x, int B, int h, int w, float* delta, float* layer_weight, void* stream);
+int nb200_mlbw_num_layers(const nb200_model* m);
 
 /* backward_warp(c, grid, delta, delta_scale) of the learned warps (iw3/backward_warp.py:67-83,213-226):
  * c [B][3][H][W], delta [B][1][h][w] fp32 -> out [B][3][H][W] = clamp(grid_sample(c, grid + delta*delta_scale)). */

@@ -9,6 +9,7 @@
 #include "depth_kernels.h"
 #include "rowflow_kernels.h"
 #include "depth_aa_kernels.h"
+#include "mlbw_kernels.h"
 #include "swin_fused.h"
 #include "../../include/nunif_b200.h"
 #include <map>
@@ -208,6 +209,7 @@ struct CUNetW;  // cunet_model.inl
 struct DaW;     // depth_model.inl
 struct RfW;     // rowflow_model.inl
 struct AaW;     // depth_aa_model.inl
+struct MlW;     // mlbw_model.inl
 
 }  // namespace nb200
 
@@ -223,6 +225,7 @@ struct nb200_model {
     std::shared_ptr<DaW> da;
     std::shared_ptr<RfW> rf;
     std::shared_ptr<AaW> aa;
+    std::shared_ptr<MlW> ml;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
@@ -557,6 +560,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 #include "depth_model.inl"
 #include "rowflow_model.inl"
 #include "depth_aa_model.inl"
+#include "mlbw_model.inl"
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -564,7 +568,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
                                   const int64_t* numel, int no_clip, nb200_model** out) {
     NB_CHECK(out && names && data && numel, "null pointer");
-    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_DEPTH_AA, "unknown model kind");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_MLBW, "unknown model kind");
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
@@ -592,6 +596,7 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
         case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk, 0); m->scale = 1; break;
         case NB200_MODEL_DEPTH_ANYTHING_V2_B: m->da = pack_depth_anything(pk, 1); m->scale = 1; break;
         case NB200_MODEL_DEPTH_ANYTHING_V2_L: m->da = pack_depth_anything(pk, 2); m->scale = 1; break;
+        case NB200_MODEL_MLBW: m->ml = pack_mlbw(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;               // mlbw.py:41
         case NB200_MODEL_DEPTH_AA: m->aa = pack_depth_aa(pk); m->scale = 1; break;                                     // depth_aa.py:34
         case NB200_MODEL_ROW_FLOW_V3: m->rf = pack_row_flow(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;   // row_flow_v3.py:37
     }
@@ -808,6 +813,15 @@ extern "C" int nb200_depth_anything_forward(nb200_model* m, const float* x, int 
     NB_CHECK(B > 0, "empty batch");
     return depth_anything_forward(m, (cudaStream_t)stream, x, B, H, W, depth);
 }
+
+// MLBW.forward with delta_output=True (iw3/models/mlbw.py:96-127,237-245): the x components of the L flow layers and their weights
+extern "C" int nb200_mlbw_delta(nb200_model* m, const float* x, int B, int h, int w, float* delta, float* layer_weight, void* stream) {
+    NB_CHECK(m && x && delta && layer_weight, "null pointer");
+    NB_CHECK(m->kind == NB200_MODEL_MLBW && m->ml, "model is not sbs.mlbw");
+    NB_CHECK(B > 0 && h > 0 && w > 0, "empty input");
+    return mlbw_forward(m, (cudaStream_t)stream, x, B, h, w, delta, layer_weight);
+}
+extern "C" int nb200_mlbw_num_layers(const nb200_model* m) { return (m && m->kind == NB200_MODEL_MLBW && m->ml) ? m->ml->L : 0; }
 
 // DepthAA.forward / DepthAA.infer (iw3/models/depth_aa.py:46-87)
 extern "C" int nb200_depth_aa(nb200_model* m, const float* x, int B, int H, int W, int mode, float* out, void* stream) {

@@ -375,9 +375,29 @@ def gen_mlbw():
     save("mlbw", d=d, x=x, delta=delta, layer_weight=lw, left=l, right=r)
 
 
+def gen_mlbw_variants():
+    """sbs.mlbw with num_layers=4 and the `small` layout (two blocks, shift along x only): delta / layer weights of the REAL model."""
+    from nunif.models import create_model
+    import iw3.models  # noqa: F401
+    from iw3.backward_warp import make_input_tensor
+    out = {}
+    for tag, L, small, (B, h, w) in [("l4", 4, False, (1, 70, 130)), ("l2s", 2, True, (2, 33, 96))]:
+        m = create_model("sbs.mlbw", num_layers=L, small=small).eval()
+        sd = synth.mlbw_state_dict(1, num_layers=L)
+        if small:
+            sd = {k: v for k, v in sd.items() if not (k.startswith("lv2.2.") or k.startswith("lv2.3."))}
+        m.load_state_dict(sd, strict=True)
+        m.delta_output = True
+        d = synth.synth_depth(7, B, h, w)
+        x = torch.stack([make_input_tensor(None, d[i], divergence=2.5, convergence=0.4, image_width=max(h, w)) for i in range(B)])
+        delta, lw = m(x)
+        out[tag + "_delta"], out[tag + "_lw"] = delta, lw                    # _forward_delta_only (:232-240): L x-flow layers + weights
+    save("mlbw_variants", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "row_flow_steps", "postprocess", "depth_scaler", "depth_aa", "mlbw"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "row_flow_steps", "postprocess", "depth_scaler", "depth_aa", "mlbw", "mlbw_variants"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -400,3 +420,5 @@ if __name__ == "__main__":
         gen_depth_aa()
     if "mlbw" in which:
         gen_mlbw()
+    if "mlbw_variants" in which:
+        gen_mlbw_variants()

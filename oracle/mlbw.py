@@ -15,10 +15,13 @@ MOD = 4
 
 
 def _window_mha(sd, p, x, ws, heads, shift, bias):
-    """WindowMHA2d (nunif/modules/attention.py:118-161) with shift = (shift, shift): zero padding by ws/2, attention, crop."""
-    pad = ws // 2 if shift else 0
+    """WindowMHA2d (nunif/modules/attention.py:118-161): zero padding by ws/2 in the shifted directions, attention, crop.
+    shift = bool (both directions) or (shift_h, shift_w)."""
+    sh, sw = shift if isinstance(shift, tuple) else (shift, shift)
+    ph, pw = (ws // 2 if sh else 0), (ws // 2 if sw else 0)
+    pad = ph or pw
     if pad:
-        x = F.pad(x, (pad, pad, pad, pad), mode="constant", value=0)
+        x = F.pad(x, (pw, pw, ph, ph), mode="constant", value=0)
     B, C, H, W = x.shape
     oh, ow = H // ws, W // ws
     t = x.reshape(B, C, oh, ws, ow, ws).permute(0, 2, 4, 3, 5, 1).reshape(B * oh * ow, ws * ws, C)
@@ -30,10 +33,10 @@ def _window_mha(sd, p, x, ws, heads, shift, bias):
     a = a.permute(0, 2, 1, 3).reshape(-1, ws * ws, C)
     a = F.linear(a, sd[p + "mha.head_proj.weight"], sd[p + "mha.head_proj.bias"])
     a = a.reshape(B, oh, ow, ws, ws, C).permute(0, 5, 1, 3, 2, 4).reshape(B, C, H, W)
-    return a[:, :, pad:-pad, pad:-pad] if pad else a
+    return a[:, :, ph:a.shape[2] - ph, pw:a.shape[3] - pw] if pad else a
 
 
-def mlbw_delta(sd, x, num_layers=2):
+def mlbw_delta(sd, x, num_layers=2, small=False):
     """MLBW._forward in eval mode: x B,3,H,W -> (delta B,L,H,W ; layer_weight B,L,H,W softmax over L)."""
     H, W = x.shape[2:]
     pad_w, pad_h = MOD * PACK - W % (MOD * PACK), MOD - H % MOD
@@ -43,7 +46,7 @@ def mlbw_delta(sd, x, num_layers=2):
     x1 = F.leaky_relu(F.conv2d(F.pad(x, (4, 4, 0, 0), mode="replicate"), sd["lv1_in.1.weight"], sd["lv1_in.1.bias"]), 0.2)
     B, C1, Hp, Wp = x1.shape
     t = x1.reshape(B, C1, Hp, 1, Wp // PACK, PACK).permute(0, 1, 3, 5, 2, 4).reshape(B, C1 * PACK, Hp, Wp // PACK)
-    for i, shift in enumerate((True, False, True, False)):
+    for i, shift in enumerate(((False, True), False) if small else (True, False, True, False)):       # mlbw.py:53-64
         p = f"lv2.{i}."
         t = t + _window_mha(sd, p + "mha.", t, 4, num_layers, shift, window_bias(sd, p + "bias.", 4))
         m = F.gelu(F.conv2d(t, sd[p + "conv_mlp.0.weight"], sd[p + "conv_mlp.0.bias"]))

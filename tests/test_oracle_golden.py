@@ -316,6 +316,22 @@ def test_row_flow_steps_oracle_matches_reference():
         assert float((l - t(g["b_left"])).abs().max()) < 1e-5 and torch.equal(r, t(g["b_right"]))
 
 
+def test_mlbw_variants_oracle_matches_reference():
+    """sbs.mlbw with 4 layers and the `small` layout against the real reference model (tests/golden/mlbw_variants.npz)."""
+    from oracle import mlbw as om
+    from oracle.row_flow import make_input
+    g = load_golden("mlbw_variants")
+    for tag, L, small, (B, h, w) in [("l4", 4, False, (1, 70, 130)), ("l2s", 2, True, (2, 33, 96))]:
+        sd = synth.mlbw_state_dict(1, num_layers=L)
+        if small:
+            sd = {k: v for k, v in sd.items() if not (k.startswith("lv2.2.") or k.startswith("lv2.3."))}
+        x = make_input(synth.synth_depth(7, B, h, w), 2.5, 0.4)
+        with torch.no_grad():
+            delta, lw = om.mlbw_delta(sd, x, num_layers=L, small=small)
+        assert float((delta - t(g[tag + "_delta"])).abs().max()) < 1e-4, tag
+        assert float((lw - t(g[tag + "_lw"])).abs().max()) < 1e-5, tag
+
+
 def _pp_kwargs(kw):
     kw = dict(kw)
     if "anaglyph" in kw:
