@@ -572,7 +572,7 @@ def run_b200(args):
     peaks, peak_src = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])     # kernels timed inside a long step: the sustained figure
     total_prof_ms = sum(v["ms"] for v in prof.values())
-    KERNEL_OF = {"fused_attn": "swin_attn_fused_kernel (tcgen05 qkv GEMM + window attention, q/k/v in shared memory)",
+    KERNEL_OF = {"fused_attn": "swin_attn_tc_kernel (tcgen05 qkv GEMM, QK^T and PV; q/k/v/S/P in shared / tensor memory)",
                  "fused_mlp": "swin_mlp_fused2_kernel / swin_mlp_fused_kernel (tcgen05 [proj +] fc1 + GELU + fc2, hidden in smem/TMEM)",
                  "gemm": "gemm_conv_persistent (tcgen05 implicit GEMM: convs, patch up/down, proj of the C=192 blocks, to_image)"}
 

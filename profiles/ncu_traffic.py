@@ -1,6 +1,6 @@
 """Turn an `ncu --set full` capture of the shipped kernels into the numbers bench.py reports as `roofline.traffic`.
 
-  gpurun:  ncu --set full --clock-control none --import-source on -k regex:'swin_attn_fused|swin_mlp_fused|gemm_conv_persistent' \
+  gpurun:  ncu --set full --clock-control none --import-source on -k regex:'swin_attn_tc|swin_mlp_fused|gemm_conv_persistent' \
                -s <skip> -c <n> -o gpurun_out/r2_fused python profiles/one_frame.py 4k
   here:    ncu -i gpurun_out/r2_fused.ncu-rep --page raw --csv > profiles/r2/fused_ncu_raw.csv
            python profiles/ncu_traffic.py profiles/r2/fused_ncu_raw.csv profiles/r2/ncu_traffic.json
@@ -12,7 +12,7 @@ import json
 import re
 import sys
 
-CLASSES = {"fused_attn": r"swin_attn_fused_kernel", "fused_mlp": r"swin_mlp_fused2?_kernel", "gemm": r"gemm_conv_persistent"}
+CLASSES = {"fused_attn": r"swin_attn_tc_kernel|swin_attn_fused_kernel", "fused_mlp": r"swin_mlp_fused2?_kernel", "gemm": r"gemm_conv_persistent"}
 WANT = {
     "dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dram_write_bytes", "gpu__time_duration.sum": "duration_ns",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
