@@ -364,3 +364,84 @@ def mlbw_state_dict(seed=0, num_layers=2):
     sd["lv1_out.1.weight"] = rn(2 * num_layers, c1, 1, 9, std=1.5 / (9 * c1) ** 0.5)
     sd["lv1_out.1.bias"] = rn(2 * num_layers, std=0.1)
     return sd
+
+
+ZOED_N = dict(dim=1024, depth=24, heads=16, hooks=(5, 11, 17, 23), oc=(256, 512, 1024, 1024), feat=256, old_grid=24)
+ZOED_MINI = dict(dim=256, depth=4, heads=4, hooks=(0, 1, 2, 3), oc=(64, 128, 256, 256), feat=128, old_grid=6)
+
+
+def zoedepth_state_dict(seed=0, cfg=None):
+    """Seeded ZoeD_N weights with the upstream checkpoint key names (ZoeD_M12_N.pt: `core.core.pretrained.model.*` = timm
+    BEiT-L/16, `core.core.pretrained.act_postprocess*` / `core.core.scratch.*` = MiDaS DPT head, the rest = ZoeDepth bins
+    head).  No checkpoint can be downloaded here; gains keep activations O(1) through the blocks and give a metric depth
+    map that varies over the image.  `cfg`: ZOED_N (default) or ZOED_MINI (fast tests, same code path)."""
+    cfg = cfg or ZOED_N
+    dim, depth, heads, oc, feat, grid = cfg["dim"], cfg["depth"], cfg["heads"], cfg["oc"], cfg["feat"], cfg["old_grid"]
+    g = torch.Generator().manual_seed(30_000 + seed)
+
+    def rn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g) * std
+
+    def conv(name, cout, cin, k, gain=1.0, bias=0.02, bias_mean=0.0):
+        sd[name + ".weight"] = rn(cout, cin, k, k, std=gain / (cin * k * k) ** 0.5)
+        sd[name + ".bias"] = bias_mean + rn(cout, std=bias)
+
+    sd = {}
+    bb, pp, sc = "core.core.pretrained.model.", "core.core.pretrained.", "core.core.scratch."
+    sd[bb + "cls_token"] = rn(1, 1, dim, std=0.5)
+    sd[bb + "patch_embed.proj.weight"] = rn(dim, 3, 16, 16, std=2.0 / (3 * 16 * 16) ** 0.5)
+    sd[bb + "patch_embed.proj.bias"] = rn(dim, std=0.2)
+    nrd = (2 * grid - 1) ** 2 + 3
+    for i in range(depth):
+        p = f"{bb}blocks.{i}."
+        sd[p + "gamma_1"] = 0.5 + rn(dim, std=0.1)
+        sd[p + "gamma_2"] = 0.5 + rn(dim, std=0.1)
+        sd[p + "norm1.weight"] = 1.0 + rn(dim, std=0.1)
+        sd[p + "norm1.bias"] = rn(dim, std=0.05)
+        sd[p + "attn.q_bias"] = rn(dim, std=0.05)
+        sd[p + "attn.v_bias"] = rn(dim, std=0.05)
+        sd[p + "attn.relative_position_bias_table"] = rn(nrd, heads, std=0.8)
+        sd[p + "attn.qkv.weight"] = rn(3 * dim, dim, std=1.2 / dim ** 0.5)
+        sd[p + "attn.proj.weight"] = rn(dim, dim, std=1.0 / dim ** 0.5)
+        sd[p + "attn.proj.bias"] = rn(dim, std=0.02)
+        sd[p + "norm2.weight"] = 1.0 + rn(dim, std=0.1)
+        sd[p + "norm2.bias"] = rn(dim, std=0.05)
+        sd[p + "mlp.fc1.weight"] = rn(4 * dim, dim, std=1.0 / dim ** 0.5)
+        sd[p + "mlp.fc1.bias"] = rn(4 * dim, std=0.02)
+        sd[p + "mlp.fc2.weight"] = rn(dim, 4 * dim, std=1.0 / (4 * dim) ** 0.5)
+        sd[p + "mlp.fc2.bias"] = rn(dim, std=0.02)
+    for i, c in enumerate(oc):
+        p = f"{pp}act_postprocess{i + 1}."
+        sd[p + "0.project.0.weight"] = rn(dim, 2 * dim, std=1.0 / (2 * dim) ** 0.5)
+        sd[p + "0.project.0.bias"] = rn(dim, std=0.02)
+        conv(p + "3", c, dim, 1, gain=1.5)
+        sd[f"{sc}layer{i + 1}_rn.weight"] = rn(feat, c, 3, 3, std=1.0 / (9 * c) ** 0.5)
+    p = pp + "act_postprocess1.4"
+    sd[p + ".weight"], sd[p + ".bias"] = rn(oc[0], oc[0], 4, 4, std=1.0 / oc[0] ** 0.5), rn(oc[0], std=0.02)
+    p = pp + "act_postprocess2.4"
+    sd[p + ".weight"], sd[p + ".bias"] = rn(oc[1], oc[1], 2, 2, std=1.0 / oc[1] ** 0.5), rn(oc[1], std=0.02)
+    conv(pp + "act_postprocess4.4", oc[3], oc[3], 3)
+    for r in (1, 2, 3, 4):
+        p = f"{sc}refinenet{r}."
+        conv(p + "out_conv", feat, feat, 1)
+        for u in (1, 2):
+            for cv in (1, 2):
+                conv(p + f"resConfUnit{u}.conv{cv}", feat, feat, 3, gain=0.7)
+    conv(sc + "output_conv.0", feat // 2, feat, 3)
+    conv(sc + "output_conv.2", 32, feat // 2, 3, gain=1.4, bias=0.05, bias_mean=0.2)
+    sd[sc + "output_conv.4.weight"] = rn(1, 32, 1, 1, std=1.0 / 32 ** 0.5).abs()
+    sd[sc + "output_conv.4.bias"] = torch.full((1,), 0.3)
+    # bins head (zoedepth_v1.py): conv2, SeedBinRegressorUnnormed (mlp_dim 256), Projector (mlp_dim 128), AttractorLayerUnnormed
+    conv("conv2", feat, feat, 1)
+    conv("seed_bin_regressor._net.0", 256, feat, 1, gain=1.4)
+    conv("seed_bin_regressor._net.2", 64, 256, 1, gain=2.0, bias=1.0, bias_mean=1.0)
+    conv("seed_projector._net.0", 128, feat, 1, gain=1.4)
+    conv("seed_projector._net.2", 128, 128, 1, gain=1.4)
+    for i, na in enumerate((16, 8, 4, 1)):
+        conv(f"projectors.{i}._net.0", 128, feat, 1, gain=1.4)
+        conv(f"projectors.{i}._net.2", 128, 128, 1, gain=1.4)
+        conv(f"attractors.{i}._net.0", 128, 128, 1, gain=1.4)
+        conv(f"attractors.{i}._net.2", na, 128, 1, gain=2.0, bias=1.0, bias_mean=1.0)
+    conv("conditional_log_binomial.mlp.0", (33 + 128) // 2, 33 + 128, 1, gain=1.4)
+    conv("conditional_log_binomial.mlp.2", 4, (33 + 128) // 2, 1, gain=2.0, bias=0.5)
+    return sd

@@ -420,3 +420,84 @@ def test_mlbw_oracle_matches_reference():
         l = om.apply_divergence_mlbw(sd, c, t(g["d"]), 2.0, 0.5, -1)
         r = om.apply_divergence_mlbw(sd, c, t(g["d"]), 2.0, 0.5, 1)
         assert float((l - t(g["left"])).abs().max()) < 1e-5 and float((r - t(g["right"])).abs().max()) < 1e-5
+
+
+def _zoe_to_hf(sd, cfg):
+    """oracle (upstream ZoeD_M12_N.pt key names) -> transformers.ZoeDepthForDepthEstimation key names (the published
+    conversion table: q/k/v split of attn.qkv, gamma -> lambda, act_postprocess -> reassemble stage, refinenet{4-i} ->
+    fusion layer i, output_conv -> relative_head, _net.{0,2} -> conv{1,2})."""
+    out = {}
+    bb, pp, sc = "core.core.pretrained.model.", "core.core.pretrained.", "core.core.scratch."
+    dim = cfg["dim"]
+    out["backbone.embeddings.cls_token"] = sd[bb + "cls_token"]
+    out["backbone.embeddings.patch_embeddings.projection.weight"] = sd[bb + "patch_embed.proj.weight"]
+    out["backbone.embeddings.patch_embeddings.projection.bias"] = sd[bb + "patch_embed.proj.bias"]
+    for i in range(cfg["depth"]):
+        p, q = f"{bb}blocks.{i}.", f"backbone.encoder.layer.{i}."
+        out[q + "lambda_1"], out[q + "lambda_2"] = sd[p + "gamma_1"], sd[p + "gamma_2"]
+        for a, b in (("norm1", "layernorm_before"), ("norm2", "layernorm_after")):
+            out[q + b + ".weight"], out[q + b + ".bias"] = sd[p + a + ".weight"], sd[p + a + ".bias"]
+        w = sd[p + "attn.qkv.weight"]
+        for j, n in enumerate(("query", "key", "value")):
+            out[q + f"attention.attention.{n}.weight"] = w[j * dim:(j + 1) * dim]
+        out[q + "attention.attention.query.bias"] = sd[p + "attn.q_bias"]
+        out[q + "attention.attention.value.bias"] = sd[p + "attn.v_bias"]
+        out[q + "attention.attention.relative_position_bias.relative_position_bias_table"] = sd[p + "attn.relative_position_bias_table"]
+        out[q + "attention.output.dense.weight"], out[q + "attention.output.dense.bias"] = sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]
+        out[q + "intermediate.dense.weight"], out[q + "intermediate.dense.bias"] = sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]
+        out[q + "output.dense.weight"], out[q + "output.dense.bias"] = sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]
+    for i in range(4):
+        p = f"{pp}act_postprocess{i + 1}."
+        for wb in ("weight", "bias"):
+            out[f"neck.reassemble_stage.readout_projects.{i}.0.{wb}"] = sd[p + "0.project.0." + wb]
+            out[f"neck.reassemble_stage.layers.{i}.projection.{wb}"] = sd[p + "3." + wb]
+            if i != 2:
+                out[f"neck.reassemble_stage.layers.{i}.resize.{wb}"] = sd[p + "4." + wb]
+        out[f"neck.convs.{i}.weight"] = sd[f"{sc}layer{i + 1}_rn.weight"]
+        p, q = f"{sc}refinenet{4 - i}.", f"neck.fusion_stage.layers.{i}."
+        for wb in ("weight", "bias"):
+            out[q + "projection." + wb] = sd[p + "out_conv." + wb]
+            for u in (1, 2):
+                for cv in (1, 2):
+                    out[q + f"residual_layer{u}.convolution{cv}.{wb}"] = sd[p + f"resConfUnit{u}.conv{cv}.{wb}"]
+    for wb in ("weight", "bias"):
+        for hf, up in (("conv1", "0"), ("conv2", "2"), ("conv3", "4")):
+            out[f"relative_head.{hf}.{wb}"] = sd[f"{sc}output_conv.{up}.{wb}"]
+        out["metric_head.conv2." + wb] = sd["conv2." + wb]
+        mods = ["seed_bin_regressor", "seed_projector"] + [f"projectors.{i}" for i in range(4)] + [f"attractors.{i}" for i in range(4)]
+        for m in mods:
+            out[f"metric_head.{m}.conv1.{wb}"] = sd[f"{m}._net.0.{wb}"]
+            out[f"metric_head.{m}.conv2.{wb}"] = sd[f"{m}._net.2.{wb}"]
+        for j in (0, 2):
+            out[f"metric_head.conditional_log_binomial.mlp.{j}.{wb}"] = sd[f"conditional_log_binomial.mlp.{j}.{wb}"]
+    return out
+
+
+def test_zoedepth_oracle_matches_transformers():
+    """ZoeD_N (BEiT-L + DPT + metric bins) is third-party code absent from /root/reference (torch.hub).  Pin the oracle's
+    restatement against the independent public implementation in this image (transformers), same weights, on a
+    non-square input so that the relative-position table is resampled."""
+    pytest.importorskip("transformers")
+    from transformers import ZoeDepthConfig, ZoeDepthForDepthEstimation, BeitConfig
+    from oracle import zoedepth as oz
+    cfg = oz.ZOED_MINI
+    sd = synth.zoedepth_state_dict(3, synth.ZOED_MINI)
+    hf_cfg = ZoeDepthConfig(
+        backbone_config=BeitConfig(image_size=16 * cfg["old_grid"], patch_size=16, hidden_size=cfg["dim"], num_hidden_layers=cfg["depth"],
+                                   num_attention_heads=cfg["heads"], intermediate_size=4 * cfg["dim"], use_relative_position_bias=True,
+                                   use_absolute_position_embeddings=False, use_mask_token=False, layer_scale_init_value=0.1,
+                                   reshape_hidden_states=False, layer_norm_eps=1e-6,
+                                   out_features=[f"stage{h + 1}" for h in cfg["hooks"]]),
+        neck_hidden_sizes=list(cfg["oc"]), fusion_hidden_size=cfg["feat"], bottleneck_features=cfg["feat"], readout_type="project",
+        reassemble_factors=[4, 2, 1, 0.5], num_relative_features=32, bin_embedding_dim=128, num_attractors=[16, 8, 4, 1],
+        bin_centers_type="softplus", bin_configurations=[{"n_bins": 64, "min_depth": 0.001, "max_depth": 10.0}])
+    hf = ZoeDepthForDepthEstimation(hf_cfg).eval()
+    missing, unexpected = hf.load_state_dict(_zoe_to_hf(sd, cfg), strict=False)
+    assert not unexpected and all("relative_position_index" in m or "k_idx" in m or "k_minus_1" in m for m in missing), (missing, unexpected)
+    x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = hf(pixel_values=x).predicted_depth
+        got = oz.zoedepth_forward(sd, x, cfg)[:, 0]
+    assert got.shape == want.shape == (2, 64, 96)
+    assert float(want.std()) > 0.05
+    assert float((got - want).abs().max()) < 2e-4 * float(want.abs().max())
