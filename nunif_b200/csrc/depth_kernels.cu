@@ -126,7 +126,11 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(float* __restrict__ 
 // ring; S and O live in mma.sync accumulator fragments, softmax is online in base 2 (scale*log2e folded into S).
 constexpr int FA_D = 64, FA_BM = 64, FA_BN = 64, FA_LD = FA_D + 8;   // +8 halves: conflict-free fragment loads
 
-__global__ void __launch_bounds__(128) flash_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int N, int heads) {
+// BIAS: an additive score bias [heads][N][ldb] fp32, pre-multiplied by log2(e) (BEiT relative position bias, zoe_model.inl);
+// ldb >= cdiv(N, 64) * 64 so that the tail block's loads stay in bounds (those columns are masked below)
+template <bool BIAS>
+__global__ void __launch_bounds__(128) flash_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int N, int heads,
+                                                              const float* __restrict__ bias, int ldb) {
     if (threadIdx.x == 0) NB_PDL_TRIGGER();
     extern __shared__ __align__(16) unsigned char fa_smem[];
     __half* sq = reinterpret_cast<__half*>(fa_smem);            // [64][72]  (later: the output tile)
@@ -190,11 +194,23 @@ __global__ void __launch_bounds__(128) flash_attention_kernel(const __half* __re
         }
         const bool tail = (blk + 1) * FA_BN > N;
         float mx[2] = {m[0], m[1]};
+        if (BIAS) {
+            // thread's rows q0 + warp*16 + g (+8) (clamped: rows >= N are never stored), columns blk*64 + nt*8 + 2*t4 (+1)
+            const float* b0 = bias + ((size_t)head * N + min(q0 + warp * 16 + g, N - 1)) * ldb + blk * FA_BN + 2 * t4;
+            const float* b1 = bias + ((size_t)head * N + min(q0 + warp * 16 + g + 8, N - 1)) * ldb + blk * FA_BN + 2 * t4;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 u0 = __ldg(reinterpret_cast<const float2*>(b0 + nt * 8));
+                const float2 u1 = __ldg(reinterpret_cast<const float2*>(b1 + nt * 8));
+                s[nt][0] = fmaf(s[nt][0], sl2, u0.x); s[nt][1] = fmaf(s[nt][1], sl2, u0.y);
+                s[nt][2] = fmaf(s[nt][2], sl2, u1.x); s[nt][3] = fmaf(s[nt][3], sl2, u1.y);
+            }
+        }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                float v = s[nt][r] * sl2;
+                float v = BIAS ? s[nt][r] : s[nt][r] * sl2;
                 if (tail && blk * FA_BN + nt * 8 + 2 * t4 + (r & 1) >= N) v = -1e30f;
                 s[nt][r] = v;
                 mx[r >> 1] = fmaxf(mx[r >> 1], v);
@@ -395,6 +411,7 @@ int da_add_layernorm(cudaStream_t st, float* X32, const __half* delta, const flo
                      int dim) {
     const unsigned grid = (unsigned)cdiv64(rows, 8);
     switch (dim) {
+        case 256: add_layernorm_kernel<256><<<grid, 256, 0, st>>>(X32, delta, w, b, out, rows); break;
         case 384: add_layernorm_kernel<384><<<grid, 256, 0, st>>>(X32, delta, w, b, out, rows); break;
         case 768: add_layernorm_kernel<768><<<grid, 256, 0, st>>>(X32, delta, w, b, out, rows); break;
         case 1024: add_layernorm_kernel<1024><<<grid, 256, 0, st>>>(X32, delta, w, b, out, rows); break;
@@ -404,12 +421,18 @@ int da_add_layernorm(cudaStream_t st, float* X32, const __half* delta, const flo
     return 0;
 }
 
-int da_attention(cudaStream_t st, const __half* qkv, __half* out, int B, int N, int heads) {
+int da_attention(cudaStream_t st, const __half* qkv, __half* out, int B, int N, int heads, const float* bias_log2e, int ldb) {
     const size_t smem = (size_t)(FA_BM + 4 * FA_BN) * FA_LD * sizeof(__half);
-    if (ensure_dyn_smem((const void*)flash_attention_kernel, smem)) return 1;
     const double T = (double)B * N * heads * FA_D;
-    ProfScope ps(st, PC_ATTN, 4.0 * T * N, T * 3 * 2, T * 2);
-    flash_attention_kernel<<<dim3(cdiv(N, FA_BM), heads, B), 128, smem, st>>>(qkv, out, N, heads);
+    ProfScope ps(st, PC_ATTN, 4.0 * T * N, T * 3 * 2 + (bias_log2e ? (double)heads * N * N * 4 : 0.0), T * 2);
+    if (bias_log2e) {
+        NB_CHECK(ldb % 2 == 0 && ldb >= cdiv(N, FA_BN) * FA_BN, "bias row stride must be even and cover whole 64-key blocks");
+        if (ensure_dyn_smem((const void*)flash_attention_kernel<true>, smem)) return 1;
+        flash_attention_kernel<true><<<dim3(cdiv(N, FA_BM), heads, B), 128, smem, st>>>(qkv, out, N, heads, bias_log2e, ldb);
+    } else {
+        if (ensure_dyn_smem((const void*)flash_attention_kernel<false>, smem)) return 1;
+        flash_attention_kernel<false><<<dim3(cdiv(N, FA_BM), heads, B), 128, smem, st>>>(qkv, out, N, heads, nullptr, 0);
+    }
     NB_LAUNCHED();
     return 0;
 }

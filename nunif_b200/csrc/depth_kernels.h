@@ -8,11 +8,12 @@ namespace nb200 {
 int da_patch_im2col(cudaStream_t st, const float* x, int B, int H, int W, __half* A, int kpad);
 // X32[b][0] = cls + pos[0]; X32[b][1+n] = T[b*P+n] + pos[1+n]   (T fp16 = patch GEMM output incl. bias)
 int da_assemble_tokens(cudaStream_t st, const __half* T, const float* cls, const float* pos, float* X32, int B, int P, int dim);
-// X32 += delta (fp16, may be null); out = LayerNorm(X32) * w + b (eps 1e-6) as fp16.  rows x dim, dim in {384, 768, 1024}
+// X32 += delta (fp16, may be null); out = LayerNorm(X32) * w + b (eps 1e-6) as fp16.  rows x dim, dim in {256, 384, 768, 1024}
 int da_add_layernorm(cudaStream_t st, float* X32, const __half* delta, const float* w, const float* b, __half* out, long long rows,
                      int dim);
 // softmax(q k^T / sqrt(64)) v over all N tokens of each image; qkv [B*N][3*dim] (q | k | v, head-major 64-wide), out [B*N][dim]
-int da_attention(cudaStream_t st, const __half* qkv, __half* out, int B, int N, int heads);
+// bias_log2e (optional): additive score bias [heads][N][ldb] fp32 already multiplied by log2(e), ldb >= cdiv(N,64)*64
+int da_attention(cudaStream_t st, const __half* qkv, __half* out, int B, int N, int heads, const float* bias_log2e = nullptr, int ldb = 0);
 // y = relu(x); if s: s = x0 + x   (NHWC fp16, n elements, n % 8 == 0)
 int da_relu_add(cudaStream_t st, const __half* x, const __half* x0, __half* y, __half* s, long long n);
 // bilinear, align_corners=True, NHWC fp16 [B][h][w][C] -> [B][H][W][C], C % 8 == 0

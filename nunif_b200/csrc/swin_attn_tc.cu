@@ -146,7 +146,7 @@ struct TcMaps {
 struct TcParams {
     unsigned long long* tl;
     int B, H, W, shift;
-    int nww, nwh, nwin, tiles;
+    int nww, nwh, tpi, tiles;   // tpi = tiles per image
     const float* bqkv;       // packed order
     const float* bias_tab;   // relative_position_bias_table [121][6]
     __half* att;
@@ -158,13 +158,15 @@ struct WinInfo {
 };
 // out of line: three roles decode windows once per tile; two integer divisions by run-time values are ~100 instructions inlined
 __device__ __noinline__ WinInfo win_info(const TcParams& p, int tile, int w) {
+    // tiles never straddle images (p.tpi tiles per image, the last one of every image may be partial): a window's slot in
+    // its tile - and with it the accumulation order of its PV product - depends only on its index inside its own image, so
+    // the result is bit-identical for every batch size (tests/test_gpu_models.py::test_swin_tiled_render_golden)
     WinInfo wi;
-    const int win = tile * WPT + w;
-    wi.valid = win < p.nwin;
     const int wpi = p.nww * p.nwh;
-    const int ww = wi.valid ? win : 0;
-    wi.b = ww / wpi;
-    const int rem = ww - wi.b * wpi;
+    wi.b = tile / p.tpi;
+    const int win = (tile - wi.b * p.tpi) * WPT + w;
+    wi.valid = win < wpi;
+    const int rem = wi.valid ? win : 0;
     wi.wy = rem / p.nww;
     wi.wx = rem - wi.wy * p.nww;
     wi.xs = p.shift > 0 && wi.wx == p.nww - 1;
@@ -641,8 +643,8 @@ static int launch_tc(cudaStream_t st, const FusedAttn& f) {
     p.B = f.B; p.H = f.H; p.W = f.W;
     p.shift = (WS >= f.H || WS >= f.W) ? 0 : f.shift;   // torchvision :151-155: no shift when the window covers the map
     p.nww = f.W / WS; p.nwh = f.H / WS;
-    p.nwin = f.B * p.nww * p.nwh;
-    p.tiles = (p.nwin + WPT - 1) / WPT;
+    p.tpi = (p.nww * p.nwh + WPT - 1) / WPT;
+    p.tiles = f.B * p.tpi;
     p.bqkv = f.bqkv_tc; p.bias_tab = f.bias_tab_tc; p.att = f.att;
     p.tl = g_timeline;
     if (ensure_dyn_smem((const void*)swin_attn_tc_kernel<C>, Cfg::SMEM)) return 1;

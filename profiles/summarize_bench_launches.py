@@ -26,7 +26,7 @@ print(f"timed frame: {len(frame)} launches, sum of kernel durations {tot / 1e3:.
 cls = collections.Counter()
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:48s} n={n:4d} {t / 1e3:8.3f} ms {100 * t / tot:5.1f}%")
-    c = ("gemm" if "gemm_conv" in k else "fused_attn" if "swin_attn_fused" in k else "fused_mlp" if "swin_mlp_fused" in k
+    c = ("gemm" if "gemm_conv" in k else "fused_attn" if ("swin_attn_fused" in k or "swin_attn_tc" in k) else "fused_mlp" if "swin_mlp_fused" in k
          else "window_attention" if "window_attention" in k else "stem_conv" if "stem" in k
          else "to_image" if "to_image" in k else "tile_unfold" if "unfold" in k else "tile_blend" if "blend" in k else "other")
     cls[c] += t
