@@ -30,6 +30,14 @@ WORKLOADS = {
     "swin2x_4k": dict(down=2, frame="4k", text="waifu2x swin_unet/art scale2x (SwinUNet4x.to_2x: 4x network + antialiased bicubic /2)"),
     "swin2x_8k": dict(down=2, frame="8k", text="waifu2x swin_unet/photo scale2x (SwinUNet4x.to_2x), 8K frame per GPU (configs[3])"),
 }
+# iw3 workloads (BASELINE.json configs[2] and configs[4]): a step = one batch of frames through depth model -> dilation ->
+# min/max (+ mapper) -> warp -> composed stereo frame; metric = frames/s
+IW3_WORKLOADS = {
+    "iw3_1080p": dict(frame="1080p", batch=4, depth="Any_V2_S", method="forward_fill", mapper="none", anaglyph=None, edge_dilation=[2, 1],
+                      text="iw3 Depth-Anything-V2-Small + dilate_edge [2,1] + forward_fill warp + SBS, 1080p stream (configs[2])"),
+    "iw3_4k_zoe": dict(frame="4k", batch=2, depth="ZoeD_N", method="backward", mapper="div_6", anaglyph="dubois", edge_dilation=2,
+                       text="iw3 ZoeD_N (BEiT-L) + dilate_edge 2 + backward (grid_sample) warp + dubois anaglyph, 4K stream (configs[4])"),
+}
 SWIN4X_TILE_GFLOP = 155.7           # BASELINE.md section 2 (conv 8.6 + addmm 140.1 + bmm 7.0)
 
 
@@ -334,8 +342,37 @@ def bench_iw3(dev, lib, peaks_gbs, B=4, iters=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     out["backward_dubois_4k"] = {"fps": 2 / (ms / 1e3), "ms_per_batch": ms, "batch": 2,
-                                 "note": "post-depth stages of configs[4] (dilate_edge, minmax + div_6 mapper, grid_sample warp, dubois); ZoeDepth body not built"}
-    del y, c4k, d4k
+                                 "note": "post-depth stages of configs[4] only (dilate_edge, minmax + div_6 mapper, grid_sample warp, dubois) on a synthetic depth map"}
+    del y, d4k
+    # ---- the whole per-frame path of BASELINE configs[4]: ZoeD_N (BEiT-L, seeded weights) at 384x704 + dilate_edge 2 + min/max +
+    # div_6 mapper + grid_sample warp + dubois anaglyph on two 4K frames resident in HBM (the standalone line is --workload iw3_4k_zoe)
+    from nunif_b200.iw3 import ZoeDepthModel
+    zm = ZoeDepthModel("ZoeD_N").load_state_dict(synth.zoedepth_state_dict(0), gpu=dev.index or 0)
+
+    def zoe_ana():
+        with torch.inference_mode():
+            depth = zm.infer(c4k, edge_dilation=2)
+            return stereo_sbs(c4k, depth, 2.0, 0.5, method="backward", mapper="div_6", edge_dilation=0, anaglyph="dubois")
+    for _ in range(3):
+        y = zoe_ana()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        y = zoe_ana()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    _lib.check(lib.nb200_profile_enable(1))
+    y = zoe_ana()
+    buf = ctypes.create_string_buffer(8192)
+    _lib.check(lib.nb200_profile_report(buf, 8192))
+    _lib.check(lib.nb200_profile_enable(0))
+    prof = json.loads(buf.value.decode())
+    out["zoe_anaglyph_4k"] = {"fps": 2 / (ms / 1e3), "ms_per_batch": ms, "batch": 2,
+                              "depth_model": "ZoeD_N = BEiT-L/16 + DPT + metric bins (seeded random weights), 384x704 network input",
+                              "kernel_classes_ms": {kk: round(v["ms"], 4) for kk, v in prof.items()}}
+    del y, c4k, zm
     # ---- the same path end to end from HOST uint8 frames (video.py to_tensor / from_tensor edges): pinned uint8 HWC in,
     # H2D, uint8->float CHW, depth, warp, SBS, float->uint8 HWC, D2H of the SBS frames
     from nunif_b200.iw3 import hwc_to_chw_float, chw_float_to_hwc
@@ -448,6 +485,216 @@ def bench_upcunet(dev, lib, x, iters=3):
             "model_tflops_per_sec": 180 * 81.9 / 1e3 / (ms / 1e3),
             "gemm_tflops_per_sec": gemm["work"] / (gemm["ms"] / 1e3) / 1e12 if gemm["ms"] else None,
             "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
+
+
+def _iw3_models(wl, dev=None):
+    """(state_dict, engine depth model or None) for an iw3 workload."""
+    from nunif_b200 import synth
+    sd = synth.zoedepth_state_dict(0) if wl["depth"] == "ZoeD_N" else synth.depth_anything_v2_state_dict(0)
+    if dev is None:
+        return sd, None
+    from nunif_b200.iw3 import DepthAnythingModel, ZoeDepthModel
+    gpu = dev.index or 0
+    dm = ZoeDepthModel("ZoeD_N").load_state_dict(sd, gpu=gpu) if wl["depth"] == "ZoeD_N" else DepthAnythingModel().load_state_dict(sd, gpu=gpu)
+    return sd, dm
+
+
+def iw3_cpu_frames(wl, n_frames, threads):
+    """The reference algorithm of an iw3 workload on the CPU (oracle port, fp32): n_frames frames through depth network ->
+    dilate_edge -> min/max (+ mapper) -> warp -> composed frame.  Returns seconds."""
+    import numpy as np
+    import torch
+    from nunif_b200 import synth
+    from oracle import iw3 as oiw3, frames as ofr
+    torch.set_num_threads(threads)
+    h, w = FRAME[wl["frame"]]
+    sd, _ = _iw3_models(wl)
+    c = torch.stack([synth.synth_image(50 + i, 3, h, w, smooth=False) for i in range(n_frames)])
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        if wl["depth"] == "ZoeD_N":
+            from oracle import zoedepth as oz
+            depth = oz.batch_infer(sd, c, flip_aug=False, edge_dilation=wl["edge_dilation"])
+        else:
+            from oracle import depth_anything as oda
+            x = torch.from_numpy(np.ascontiguousarray(ofr.batch_preprocess(c.numpy(), 392)))
+            depth = oiw3.dilate_edge(oda.depth_anything_forward(sd, x).unsqueeze(1), wl["edge_dilation"])
+        depth = oiw3.mapper(oiw3.minmax_normalize(depth), wl["mapper"])
+        if wl["method"] == "backward":
+            left, right = oiw3.apply_divergence_grid_sample(c, depth, 2.0, 0.5)
+        else:
+            left, right = oiw3.forward_warp(c, depth, 2.0, 0.5, fill=True)
+        ys = [oiw3.dubois(lf, rt) if wl["anaglyph"] else oiw3.sbs(lf, rt) for lf, rt in zip(left, right)]
+        assert len(ys) == n_frames
+        return time.perf_counter() - t0
+
+
+def iw3_cpu_baseline_object(wl, n_frames=1):
+    cores = host_cores()
+    threads = min(cores, 32)          # one torch process stops scaling on these layer sizes well before 128 threads
+    t = iw3_cpu_frames(wl, n_frames, threads)
+    return t, {"value": n_frames / t, "unit": "frames/s", "cores": threads, "kind": "port", "host_cores": cores,
+               "sample": f"{n_frames} {wl['frame']} frame(s) through the oracle port of the whole path (oracle/zoedepth.py | depth_anything.py, "
+                         f"iw3.py; torch-CPU fp32, {threads} threads), {t:.1f} s"}
+
+
+def run_iw3_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = IW3_WORKLOADS[args.workload]
+    ts, cb = [], None
+    for _ in range(max(1, min(args.steps, 3))):      # bounded: a step is ONE frame on the host cores
+        t, cb = iw3_cpu_baseline_object(wl, 1)
+        ts.append(t)
+    t = sum(ts) / len(ts)
+    cb["value"] = 1.0 / t
+    h, w = FRAME[wl["frame"]]
+    print(json.dumps({
+        "impl": "reference", "metric": "iw3_frames_per_sec", "value": 1.0 / t, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(ts),
+        "warmup": 0, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{wl['text']}, {w}x{h} frames, 1 frame per step (bounded sample of the stream)",
+                                        "workload_key": args.workload},
+        "cpu_baseline": cb, "e2e": {"value": 1.0 / t, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def _init_b200(args):
+    import torch
+    import torch.distributed as dist
+    from nunif_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    lib = _lib.lib()
+    _lib.check(lib.nb200_check_device(local))
+    return world, rank, local, dev, lib
+
+
+def run_b200_iw3(args):
+    """--workload iw3_1080p | iw3_4k_zoe: frame-parallel stream, B frames per GPU per step (weak scaling, no data-path collective;
+    every rank packs the same seeded weights).  `value`: frames resident in HBM as float CHW, device-timed.  `e2e`: pinned uint8
+    HWC frames on the host -> FrameBatchPipeline (H2D | compute | D2H streams, ticket order) -> uint8 stereo frames on the host."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from nunif_b200 import synth, _lib
+    from nunif_b200.iw3 import stereo_sbs
+    from nunif_b200.nunif.video import FrameBatchPipeline
+    world, rank, local, dev, lib = _init_b200(args)
+    wl = IW3_WORKLOADS[args.workload]
+    h, w = FRAME[wl["frame"]]
+    B = wl["batch"]
+    _, dm = _iw3_models(wl, dev)
+    c = torch.stack([synth.synth_image(50 + 16 * rank + i, 3, h, w, smooth=False) for i in range(B)]).to(dev)
+
+    def frames_to_stereo(xf):
+        depth = dm.infer(xf, edge_dilation=wl["edge_dilation"])
+        return stereo_sbs(xf, depth, 2.0, 0.5, method=wl["method"], mapper=wl["mapper"], edge_dilation=0, anaglyph=wl["anaglyph"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.inference_mode():
+        for _ in range(args.warmup):
+            y = frames_to_stereo(c)
+        barrier()
+        launches0 = lib.nb200_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            e0.record()
+            for _ in range(args.steps):
+                y = frames_to_stereo(c)
+            e1.record()
+            barrier()
+        launches = lib.nb200_launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+        out_shape = list(y.shape)
+        # ---- end to end from host uint8 frames
+        u8_in = (c.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).cpu().pin_memory()
+        frames_host = [u8_in[i] for i in range(B)]
+        pipe = FrameBatchPipeline(frames_to_stereo, B, dev, depth=3, copy_output=False)
+        e2e_steps = max(2, min(args.steps, 10))
+        done = 0
+        for i in range(3 * B):
+            done += len(pipe(frames_host[i % B]))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps * B):
+            done += len(pipe(frames_host[i % B]))
+        done += len(pipe.finish())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert done == (e2e_steps + 3) * B, done
+        # ---- kernel classes
+        _lib.check(lib.nb200_profile_enable(1))
+        y = frames_to_stereo(c)
+        buf = ctypes.create_string_buffer(8192)
+        _lib.check(lib.nb200_profile_report(buf, 8192))
+        _lib.check(lib.nb200_profile_enable(0))
+        prof = json.loads(buf.value.decode())
+    t = torch.tensor([ms, dt * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    fps = world * args.steps * B / (ms / 1e3)
+    fps_e2e = world * e2e_steps * B / (ms_e2e / 1e3)
+    peaks, peak_src = load_peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    total = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    if dom in ("gemm", "window_attention"):
+        ach = d["work"] / (d["ms"] / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf}
+    else:
+        ach = d["work"] / (d["ms"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
+    roof.update({"kernel": {"gemm": "gemm_conv_persistent (tcgen05 implicit GEMM: every Linear / conv of the depth network)",
+                            "window_attention": "flash_attention_kernel (mma.sync, d = 64, relative-position bias for BEiT)"}.get(dom, dom),
+                 "class": dom, "launches": d.get("launches"), "avg_launch_us": d["ms"] * 1e3 / max(1, d.get("launches", 1)),
+                 "share_of_step": d["ms"] / total, "peak_source": f"{peak_src} MEASURED_PEAKS.json", "traffic": None,
+                 "note": "achieved = algorithmic FLOPs (2*M*N*K per GEMM launch; 4*T*N*d per attention launch) or bytes of every launch of the "
+                         "dominant kernel class in one step / their CUDA-event time (nb200_profile_report)"})
+    line = {
+        "metric": "iw3_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"{wl['text']}, {w}x{h} frames, {B} frames/GPU/step", "workload_key": args.workload,
+                   "parallelism": f"frame-parallel x{world} (no data-path collective)", "weights": "random-init seed 0 (nunif_b200.synth)",
+                   "l2": "frames + activations per step exceed the 126 MB L2; no explicit flush", "output_shape": out_shape,
+                   "input_megapixels_per_sec": fps * h * w / 1e6},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(u8_in.numel()),
+                "d2h_bytes_per_step": int(out_shape[0] * out_shape[1] * out_shape[2] * out_shape[3]), "steps": e2e_steps,
+                "note": "pinned uint8 HWC frames -> FrameBatchPipeline depth 3 (H2D | uint8->float, depth, warp, compose, float->uint8 | D2H on "
+                        "three streams, ticket order) -> uint8 frames on the host; host wall clock incl. the final drain"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof,
+        "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = iw3_cpu_baseline_object(wl, 1)[1]
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_b200(args):
@@ -656,11 +903,15 @@ def main():
     ap.add_argument("--compile", action="store_true", help="--impl torch_gpu: wrap the forward in torch.compile")
     ap.add_argument("--cpu-worker", nargs=2, type=int, metavar=("TILES", "THREADS"), help=argparse.SUPPRESS)
     ap.add_argument("--frame", default=None, choices=list(FRAME), help="frame size (default: the workload's)")
-    ap.add_argument("--workload", default="swin4x_4k", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="swin4x_4k", choices=list(WORKLOADS) + list(IW3_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.cpu_worker:
         cpu_worker_main(*args.cpu_worker)
+    elif args.workload in IW3_WORKLOADS:
+        if args.impl == "torch_gpu":
+            raise SystemExit("--impl torch_gpu is defined for the waifu2x workloads")
+        run_iw3_reference(args) if args.impl == "reference" else run_b200_iw3(args)
     elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "torch_gpu":

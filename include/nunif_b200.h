@@ -87,7 +87,11 @@ enum {
     NB200_MODEL_DEPTH_ANYTHING_V2_B = 8,   /* Any_V2_B: ViT-B encoder, 128 head features */
     NB200_MODEL_DEPTH_ANYTHING_V2_L = 9,   /* Any_V2_L: ViT-L encoder (24 blocks), 256 head features */
     NB200_MODEL_DEPTH_AA = 10,             /* iw3.depth_aa, learned anti-aliasing of the depth map (iw3/models/depth_aa.py) */
-    NB200_MODEL_MLBW = 11                  /* sbs.mlbw, multi-layer learned stereo warp, num_layers 2 | 4 (iw3/models/mlbw.py) */
+    NB200_MODEL_MLBW = 11,                 /* sbs.mlbw, multi-layer learned stereo warp, num_layers 2 | 4 (iw3/models/mlbw.py) */
+    /* ZoeD_N metric depth: third-party net the reference loads through torch.hub "nagadomi/ZoeDepth_iw3" (iw3/zoedepth_model.py:151-157);
+     * state_dict keys of ZoeD_M12_N.pt (`core.core.pretrained.*`, `core.core.scratch.*`, `conv2`, `seed_bin_regressor`, ...).
+     * The widths are read off the tensor sizes (BEiT-L/16 for the released checkpoint). */
+    NB200_MODEL_ZOEDEPTH_N = 12
 };
 
 /* Create a model from named fp32 host tensors using the reference's state_dict
@@ -132,6 +136,11 @@ int nb200_tiled_render_host(nb200_model* m, const float* x_host, int C, int H, i
  * -> depth [B][H][W] fp32 (relative inverse depth, larger = nearer). */
 int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth,
                                  void* stream);
+
+/* ZoeDepth.forward(x)['metric_depth'] as called by zoedepth_model._forward (iw3/zoedepth_model.py:23-27):
+ * x [B][3][H][W] fp32, normalised (x - 0.5) / 0.5 and reflection padded (nb200_zoe_preprocess), H and W multiples of 32
+ * -> depth [B][H][W] fp32 (metric depth, larger = farther; batch_infer negates it, zoedepth_model.py:124-130). */
+int nb200_zoedepth_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth, void* stream);
 
 /* iw3.depth_aa (iw3/models/depth_aa.py:46-87; applied by batch_infer when depth_aa is set, iw3/depth_anything_model.py:153-154):
  * x [B][1][H][W] fp32 -> out, same shape.  mode 0 = forward in eval mode (clamp to [0,1]), 1 = infer (normalise by the
@@ -321,6 +330,7 @@ int nb200_equirectangular(const float* c, int C, int H, int W, float* out, void*
  * bench.py for the live roofline figure.  report writes a JSON object
  * {"gemm": {"launches": n, "ms": t, "work": flops_or_bytes}, ...} and synchronises the device. */
 int nb200_tune_set(int key, int value);   /* GEMM scheduling knobs for profiles/gemm_bench.py */
+int nb200_debug_tap(int id, void* dev_buf, size_t capacity);  /* copy intermediate `id` of nb200_zoedepth_forward to dev_buf (profiles/debug_zoe.py) */
 int nb200_debug_timeline(void* dev_buf);  /* per-role clock64 timeline of CTA 0 (profiles/gemm_timeline.py) */
 int nb200_profile_enable(int on);
 int nb200_profile_report(char* buf, size_t cap);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "nb200_tiled_render": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "nb200_tiled_render_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "nb200_depth_anything_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "nb200_zoedepth_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "nb200_depth_aa": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "nb200_mlbw_delta": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nb200_mlbw_num_layers": (c_int, [c_void_p]),
@@ -94,6 +95,7 @@ SIGNATURES = {
                                     c_void_p]),
     "nb200_tune_set": (c_int, [c_int, c_int]),
     "nb200_debug_timeline": (c_int, [c_void_p]),
+    "nb200_debug_tap": (c_int, [c_int, c_void_p, ctypes.c_size_t]),
     "nb200_profile_enable": (c_int, [c_int]),
     "nb200_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "nb200_profile_dump": (c_int, [c_char_p, c_size_t]),

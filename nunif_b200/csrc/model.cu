@@ -10,6 +10,7 @@
 #include "rowflow_kernels.h"
 #include "depth_aa_kernels.h"
 #include "mlbw_kernels.h"
+#include "zoe_kernels.h"
 #include "swin_fused.h"
 #include "../../include/nunif_b200.h"
 #include <map>
@@ -210,6 +211,7 @@ struct DaW;     // depth_model.inl
 struct RfW;     // rowflow_model.inl
 struct AaW;     // depth_aa_model.inl
 struct MlW;     // mlbw_model.inl
+struct ZoeW;    // zoe_model.inl
 
 }  // namespace nb200
 
@@ -226,6 +228,7 @@ struct nb200_model {
     std::shared_ptr<RfW> rf;
     std::shared_ptr<AaW> aa;
     std::shared_ptr<MlW> ml;
+    std::shared_ptr<ZoeW> zoe;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     cudaStream_t copy_stream = nullptr;   // D2H side stream of nb200_tiled_render_host
@@ -557,10 +560,22 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 }  // namespace nb200
 
 #include "cunet_model.inl"
+// debug tap (nb200_debug_tap): stage `g_tap_id` of the next ZoeDepth forward is copied to `g_tap_buf` (profiles/debug_zoe.py)
+static int g_tap_id = -1;
+static void* g_tap_buf = nullptr;
+static size_t g_tap_cap = 0;
+static int tap_copy(cudaStream_t st, int id, const void* src, size_t bytes) {
+    if (id != g_tap_id || !g_tap_buf) return 0;
+    NB_CHECK(bytes <= g_tap_cap, "debug tap buffer too small: need " + std::to_string(bytes) + " bytes");
+    NB_CUDA(cudaMemcpyAsync(g_tap_buf, src, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 #include "depth_model.inl"
 #include "rowflow_model.inl"
 #include "depth_aa_model.inl"
 #include "mlbw_model.inl"
+#include "zoe_model.inl"
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -568,7 +583,7 @@ static int swin_forward(nb200_model* m, cudaStream_t st, const __half* x, int n,
 extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* names, const float* const* data,
                                   const int64_t* numel, int no_clip, nb200_model** out) {
     NB_CHECK(out && names && data && numel, "null pointer");
-    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_MLBW, "unknown model kind");
+    NB_CHECK(kind >= NB200_MODEL_UPCUNET && kind <= NB200_MODEL_ZOEDEPTH_N, "unknown model kind");
     int dev = 0;
     NB_CUDA(cudaGetDevice(&dev));
     if (nb200_check_device(dev)) return 1;
@@ -596,6 +611,7 @@ extern "C" int nb200_model_create(int kind, int n_tensors, const char* const* na
         case NB200_MODEL_DEPTH_ANYTHING_V2_S: m->da = pack_depth_anything(pk, 0); m->scale = 1; break;
         case NB200_MODEL_DEPTH_ANYTHING_V2_B: m->da = pack_depth_anything(pk, 1); m->scale = 1; break;
         case NB200_MODEL_DEPTH_ANYTHING_V2_L: m->da = pack_depth_anything(pk, 2); m->scale = 1; break;
+        case NB200_MODEL_ZOEDEPTH_N: m->zoe = pack_zoedepth(pk); m->scale = 1; break;                                   // zoedepth_model.py:151-157
         case NB200_MODEL_MLBW: m->ml = pack_mlbw(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;               // mlbw.py:41
         case NB200_MODEL_DEPTH_AA: m->aa = pack_depth_aa(pk); m->scale = 1; break;                                     // depth_aa.py:34
         case NB200_MODEL_ROW_FLOW_V3: m->rf = pack_row_flow(pk); m->scale = 1; m->offset = 32; m->blend = 4; break;   // row_flow_v3.py:37
@@ -804,6 +820,20 @@ extern "C" int nb200_tiled_render_host(nb200_model* m, const float* x_host, int 
     NB_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
     NB_CUDA(cudaEventDestroy(ev_end));
     return rc;   // scratch_guard frees xd / od behind the last copy (stream-ordered)
+}
+
+// debug: copy intermediate `id` of the following nb200_zoedepth_forward calls into dev_buf (capacity bytes); id < 0 disables
+extern "C" int nb200_debug_tap(int id, void* dev_buf, size_t capacity) {
+    g_tap_id = id; g_tap_buf = dev_buf; g_tap_cap = capacity;
+    return 0;
+}
+
+// ZoeDepth.forward(x)['metric_depth'] (what zoedepth_model._forward calls, iw3/zoedepth_model.py:23-27)
+extern "C" int nb200_zoedepth_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth, void* stream) {
+    NB_CHECK(m && x && depth, "null pointer");
+    NB_CHECK(m->zoe, "model is not a ZoeDepth network");
+    NB_CHECK(B > 0, "empty batch");
+    return zoedepth_forward(m, (cudaStream_t)stream, x, B, H, W, depth);
 }
 
 // DepthAnythingV2.forward (what DepthAnythingModel._forward calls, iw3/depth_anything_model.py:113-119)

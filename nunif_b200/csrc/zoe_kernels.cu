@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) zoe_clb_concat_kernel(const __half* __res
 }
 
 // one warp per pixel: lanes split the 80-wide dot products, then each lane owns bins k = lane and lane + 32
-__global__ void __launch_bounds__(256) zoe_clb_final_kernel(const __half* __restrict__ g, const float* __restrict__ w2, const float* __restrict__ b2,
+__global__ void __launch_bounds__(256) zoe_clb_final_kernel(const __half* __restrict__ g, int ldg, const float* __restrict__ w2, const float* __restrict__ b2,
                                                              const float* __restrict__ bins, int B, int h, int w, int H, int W, float sy,
                                                              float sx, float* __restrict__ depth) {
     if (threadIdx.x == 0) NB_PDL_TRIGGER();
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) zoe_clb_final_kernel(const __half* __rest
     const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pix >= (long long)B * H * W) return;
     const int lane = threadIdx.x & 31;
-    const __half* gp = g + (size_t)pix * 80;
+    const __half* gp = g + (size_t)pix * ldg;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = lane; c < 80; c += 32) {
         const float v = __half2float(__ldg(gp + c));
@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(256) zoe_clb_final_kernel(const __half* __rest
     for (int o = 0; o < 4; ++o) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
-        // conv output is an fp16 tensor under autocast; softplus runs in fp32
-        acc[o] = softplus(__half2float(__float2half_rn(acc[o] + sw[320 + o]))) + 1e-4f;
+        // (the reference's conv output is an fp16 tensor under autocast; the fp32 sum is kept here: these 4 values are
+        // amplified by up to 63 / min_temp ~ 3000 in the logits below, so their rounding dominates the output error)
+        acc[o] = softplus(acc[o] + sw[320 + o]) + 1e-4f;
     }
     const float p = acc[0] / (acc[0] + acc[1]);
     const float tn = acc[2] / (acc[2] + acc[3]);
@@ -348,10 +349,11 @@ int zoe_clb_concat(cudaStream_t st, const __half* act, const float* rel, const _
     return 0;
 }
 
-int zoe_clb_final(cudaStream_t st, const __half* g, const float* w2, const float* b2, const float* bins, int B, int h, int w, int H,
+int zoe_clb_final(cudaStream_t st, const __half* g, int ldg, const float* w2, const float* b2, const float* bins, int B, int h, int w, int H,
                   int W, float* depth) {
+    NB_CHECK(ldg >= 80, "hidden row stride too small");
     const long long npix = (long long)B * H * W;
-    zoe_clb_final_kernel<<<(unsigned)cdiv64(npix, 8), 256, 0, st>>>(g, w2, b2, bins, B, h, w, H, W, ac_scale(h, H), ac_scale(w, W), depth);
+    zoe_clb_final_kernel<<<(unsigned)cdiv64(npix, 8), 256, 0, st>>>(g, ldg, w2, b2, bins, B, h, w, H, W, ac_scale(h, H), ac_scale(w, W), depth);
     NB_LAUNCHED();
     return 0;
 }

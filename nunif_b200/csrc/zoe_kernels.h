@@ -14,8 +14,6 @@ int zoe_add_cast(cudaStream_t st, float* X32, const __half* delta, __half* out, 
 // bias[h][q][k] (ld = ldb floats, pre-multiplied by log2 e) = table[index(q, k)][h] for a ph x pw token grid + class token;
 // table fp32 [(2ph-1)(2pw-1) + 3][heads] (already resampled to this grid), MiDaS beit.py gen_relative_position_index
 int zoe_expand_rel_bias(cudaStream_t st, const float* table, int ph, int pw, int heads, float* bias, int ldb);
-// flash attention with an additive bias: softmax(q k^T / 8 + bias[h]) v;  qkv [B*N][3*dim], out [B*N][dim], d = 64
-int zoe_attention(cudaStream_t st, const __half* qkv, __half* out, int B, int N, int heads, const float* bias_log2e, int ldb);
 // ProjectReadout input: A[b*P+n][0..dim) = F[b][1+n][:], A[..][dim..2dim) = F[b][0][:]    (F fp16 [B][1+P][dim])
 int zoe_readout_concat(cudaStream_t st, const __half* F, int B, int P, int dim, __half* A);
 // y = e + bilinear(align_corners=True)(prev [B][h][w][C] -> [B][H][W][C]), fp16 NHWC, C % 8 == 0
@@ -29,9 +27,9 @@ int zoe_attractor(cudaStream_t st, const __half* apre, int lda, int na, const fl
 // ConditionalLogBinomial input: A[pix][0..32) = act, [32] = rel, [33..161) = bilinear(align_corners)(emb [B][h][w][128] -> H x W),
 // [161..192) = 0;  act fp16 [B][H][W][32], rel fp32 [B][H][W]
 int zoe_clb_concat(cudaStream_t st, const __half* act, const float* rel, const __half* emb, int B, int h, int w, int H, int W, __half* A);
-// g fp16 [pix][80] (GELU'd hidden) -> 4 outputs (w2 fp32 [4][80], b2 [4]) -> softplus -> p, temperature -> log-binomial
+// g fp16 [pix][ldg >= 80] (GELU'd hidden) -> 4 outputs (w2 fp32 [4][80], b2 [4]) -> softplus -> p, temperature -> log-binomial
 // softmax over 64 bins -> sum_k prob_k * bilinear(align_corners)(bins [B][h][w][64] fp32)_k -> depth fp32 [B][H][W]
-int zoe_clb_final(cudaStream_t st, const __half* g, const float* w2, const float* b2, const float* bins, int B, int h, int w, int H,
+int zoe_clb_final(cudaStream_t st, const __half* g, int ldg, const float* w2, const float* b2, const float* bins, int B, int h, int w, int H,
                   int W, float* depth);
 
 }  // namespace nb200

@@ -17,6 +17,7 @@ from .frames import hwc_to_chw_float, chw_float_to_hwc  # noqa: F401
 from .depth_anything_preprocess import batch_preprocess, preprocess_size  # noqa: F401
 from .depth_anything_model import DepthAnythingModel, DepthAnythingNet, batch_infer  # noqa: F401
 from . import zoedepth_preprocess  # noqa: F401
+from .zoedepth_model import ZoeDepthModel, ZoeDepthNet  # noqa: F401
 from .row_flow import RowFlowV3, MLBW, apply_divergence_nn_LR, apply_divergence_nn_delta, apply_divergence_nn_delta_weight  # noqa: F401
 from .depth_aa import DepthAA  # noqa: F401
 from .postprocess import postprocess_image, postprocess_padding, resize_bicubic_aa, equirectangular_projection  # noqa: F401
