@@ -53,6 +53,8 @@ class DepthAnythingNet:
     def __call__(self, x):
         _lib.require_cuda(x, "x")
         assert x.ndim == 4 and x.shape[1] == 3
+        if x.device != self.device:
+            raise RuntimeError(f"input is on {x.device} but the model's packed weights live on {self.device}")
         B, _, H, W = x.shape
         xf = x.float().contiguous()
         out = torch.empty((B, H, W), dtype=torch.float32, device=x.device)

@@ -21,11 +21,12 @@ from ..iw3.frames import hwc_to_chw_float, chw_float_to_hwc
 
 
 class _Slot:
-    __slots__ = ("h_in", "d_in", "h_out", "n", "n_out", "ready", "done", "out_shape")
+    __slots__ = ("h_in", "d_in", "h_out", "n", "n_out", "ready", "done", "out_shape", "direct")
 
     def __init__(self):
         self.h_in = self.d_in = self.h_out = None
         self.n = self.n_out = 0
+        self.direct = 0          # bit i: frame i of the batch being filled was copied straight from the caller's pinned memory
         self.ready = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.out_shape = None
@@ -73,7 +74,14 @@ class FrameBatchPipeline:
             self._slot_buffers(slot, frame)
         else:
             out = []
-        slot.h_in[self.fill].copy_(frame)            # host memcpy into the pinned batch
+        if frame.is_pinned() and frame.is_contiguous():
+            # zero-copy submit: the frame's own page-locked memory is the DMA source (a decoder writing into pinned buffers, the
+            # bench); the caller must not overwrite it before the batch it belongs to has been launched
+            with torch.cuda.stream(self.s_in):
+                slot.d_in[self.fill].copy_(frame, non_blocking=True)
+            slot.direct |= 1 << self.fill
+        else:
+            slot.h_in[self.fill].copy_(frame)        # host memcpy into the pinned batch (pageable source, e.g. a PyAV ndarray)
         self.fill += 1
         if self.fill == self.batch_size:
             self._launch(slot, self.fill)
@@ -82,8 +90,14 @@ class FrameBatchPipeline:
     def _launch(self, slot, n):
         comp = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.s_in):
-            slot.d_in[:n].copy_(slot.h_in[:n], non_blocking=True)
+            if slot.direct == 0:
+                slot.d_in[:n].copy_(slot.h_in[:n], non_blocking=True)
+            else:
+                for i in range(n):                   # frames staged on the host go now; the pinned ones are already in flight
+                    if not (slot.direct >> i) & 1:
+                        slot.d_in[i].copy_(slot.h_in[i], non_blocking=True)
             slot.ready.record(self.s_in)
+        slot.direct = 0
         comp.wait_event(slot.ready)
         with torch.inference_mode():
             x = hwc_to_chw_float(slot.d_in[:n])

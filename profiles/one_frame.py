@@ -1,5 +1,5 @@
 """Render ONE synthetic frame through the engine (for ncu captures; never a bench value).
-usage: python profiles/one_frame.py [4k|1080p] [warp|depth|upcunet]"""
+usage: python profiles/one_frame.py [4k|1080p] [warp|depth|zoe|upcunet]"""
 import os
 import sys
 import torch
@@ -27,6 +27,15 @@ elif "depth" in sys.argv:
     with torch.inference_mode():
         for _ in range(2):
             y = dam.infer(c, edge_dilation=[2, 1])
+    torch.cuda.synchronize()
+elif "zoe" in sys.argv:
+    from nunif_b200.iw3 import ZoeDepthModel
+    zm = ZoeDepthModel("ZoeD_N").load_state_dict(synth.zoedepth_state_dict(0), gpu=0)
+    c = torch.stack([synth.synth_image(50 + i, 3, h, w, smooth=False) for i in range(2)]).to(dev)
+    with torch.inference_mode():
+        for _ in range(2):
+            d = zm.infer(c, edge_dilation=2)
+            y = stereo_sbs(c, d, 2.0, 0.5, method="backward", mapper="div_6", edge_dilation=0, anaglyph="dubois")
     torch.cuda.synchronize()
 elif "upcunet" in sys.argv:
     m = create_model("waifu2x.upcunet", synth.upcunet_state_dict(0), dev)
