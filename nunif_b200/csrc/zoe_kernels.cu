@@ -182,30 +182,44 @@ __global__ void __launch_bounds__(256) zoe_attractor_kernel(const __half* __rest
     out[i] = c + delta / (float)na;
 }
 
+// one thread per (pixel, group of 8 channels): groups 0..15 = the resampled embedding, 16..19 = the activation, 20 = relative
+// depth + zeros, 21..23 = zeros (channel order chosen at pack time, zoe_model.inl)
 __global__ void __launch_bounds__(256) zoe_clb_concat_kernel(const __half* __restrict__ act, const float* __restrict__ rel,
                                                               const __half* __restrict__ emb, int B, int h, int w, int H, int W, float sy,
                                                               float sx, __half* __restrict__ A) {
     if (threadIdx.x == 0) NB_PDL_TRIGGER();
-    constexpr int KP = 192;
-    const long long total = (long long)B * H * W * KP;
+    constexpr int G = 24;
+    const long long total = (long long)B * H * W * G;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int c = (int)(i % KP);
-    const long long pix = i / KP;
-    __half v = __float2half_rn(0.f);
-    if (c < 32) v = act[(size_t)pix * 32 + c];
-    else if (c == 32) v = __float2half_rn(rel[pix]);
-    else if (c < 161) {
+    const int g = (int)(i % G);
+    const long long pix = i / G;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g < 16) {
         const int X = (int)(pix % W);
         const long long r = pix / W;
         const int Y = (int)(r % H), b = (int)(r / H);
         const Lerp ly = lerp_ac(Y, sy, h), lx = lerp_ac(X, sx, w);
-        const __half* p = emb + (size_t)b * h * w * 128 + (c - 33);
-        const float a = __half2float(p[((size_t)ly.i0 * w + lx.i0) * 128]), bq = __half2float(p[((size_t)ly.i0 * w + lx.i1) * 128]);
-        const float cc = __half2float(p[((size_t)ly.i1 * w + lx.i0) * 128]), d = __half2float(p[((size_t)ly.i1 * w + lx.i1) * 128]);
-        v = __float2half_rn(ly.l0 * (lx.l0 * a + lx.l1 * bq) + ly.l1 * (lx.l0 * cc + lx.l1 * d));
+        const __half* p = emb + (size_t)b * h * w * 128 + g * 8;
+        const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(p + ((size_t)ly.i0 * w + lx.i0) * 128));
+        const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(p + ((size_t)ly.i0 * w + lx.i1) * 128));
+        const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(p + ((size_t)ly.i1 * w + lx.i0) * 128));
+        const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(p + ((size_t)ly.i1 * w + lx.i1) * 128));
+        const __half2 *a = reinterpret_cast<const __half2*>(&v00), *bq = reinterpret_cast<const __half2*>(&v01);
+        const __half2 *c = reinterpret_cast<const __half2*>(&v10), *d = reinterpret_cast<const __half2*>(&v11);
+        __half2* o = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fa = __half22float2(a[k]), fb = __half22float2(bq[k]), fc = __half22float2(c[k]), fd = __half22float2(d[k]);
+            o[k] = __floats2half2_rn(ly.l0 * (lx.l0 * fa.x + lx.l1 * fb.x) + ly.l1 * (lx.l0 * fc.x + lx.l1 * fd.x),
+                                     ly.l0 * (lx.l0 * fa.y + lx.l1 * fb.y) + ly.l1 * (lx.l0 * fc.y + lx.l1 * fd.y));
+        }
+    } else if (g < 20) {
+        v = __ldg(reinterpret_cast<const uint4*>(act + (size_t)pix * 32 + (g - 16) * 8));
+    } else if (g == 20) {
+        v.x = (uint32_t)__half_as_ushort(__float2half_rn(__ldg(rel + pix)));
     }
-    A[i] = v;
+    *reinterpret_cast<uint4*>(A + (size_t)i * 8) = v;
 }
 
 // one warp per pixel: lanes split the 80-wide dot products, then each lane owns bins k = lane and lane + 32
@@ -222,9 +236,10 @@ __global__ void __launch_bounds__(256) zoe_clb_final_kernel(const __half* __rest
         slb[threadIdx.x] = n * logf(n) - k * logf(k) - (n - k) * logf(n - k + eps);
     }
     __syncthreads();
-    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= (long long)B * H * W) return;
     const int lane = threadIdx.x & 31;
+    const long long npix = (long long)B * H * W, wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    // persistent warps: the weight / log-binomial tables are staged once per block, not once per 8 pixels
+    for (long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += wstride) {
     const __half* gp = g + (size_t)pix * ldg;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = lane; c < 80; c += 32) {
@@ -276,6 +291,7 @@ __global__ void __launch_bounds__(256) zoe_clb_final_kernel(const __half* __rest
         den += __shfl_xor_sync(0xffffffffu, den, s);
     }
     if (lane == 0) depth[pix] = num / den;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host wrappers
@@ -343,7 +359,7 @@ int zoe_attractor(cudaStream_t st, const __half* apre, int lda, int na, const fl
 }
 
 int zoe_clb_concat(cudaStream_t st, const __half* act, const float* rel, const __half* emb, int B, int h, int w, int H, int W, __half* A) {
-    const long long total = (long long)B * H * W * 192;
+    const long long total = (long long)B * H * W * 24;
     zoe_clb_concat_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(act, rel, emb, B, h, w, H, W, ac_scale(h, H), ac_scale(w, W), A);
     NB_LAUNCHED();
     return 0;
@@ -353,7 +369,8 @@ int zoe_clb_final(cudaStream_t st, const __half* g, int ldg, const float* w2, co
                   int W, float* depth) {
     NB_CHECK(ldg >= 80, "hidden row stride too small");
     const long long npix = (long long)B * H * W;
-    zoe_clb_final_kernel<<<(unsigned)cdiv64(npix, 8), 256, 0, st>>>(g, ldg, w2, b2, bins, B, h, w, H, W, ac_scale(h, H), ac_scale(w, W), depth);
+    const long long blocks = cdiv64(npix, 8), cap = (long long)device_sm_count() * 8;
+    zoe_clb_final_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, ldg, w2, b2, bins, B, h, w, H, W, ac_scale(h, H), ac_scale(w, W), depth);
     NB_LAUNCHED();
     return 0;
 }

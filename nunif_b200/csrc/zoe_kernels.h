@@ -24,8 +24,8 @@ int zoe_softplus(cudaStream_t st, const __half* x, float* out, long long n);
 // (apre fp16, row stride lda); out[pix][k] = c_k + mean_j inv_attractor(a_j - c_k), inv_attractor(dx) = dx / (1 + 300 dx^2)
 int zoe_attractor(cudaStream_t st, const __half* apre, int lda, int na, const float* prev_bin, int B, int h, int w, int H, int W,
                   float* out);
-// ConditionalLogBinomial input: A[pix][0..32) = act, [32] = rel, [33..161) = bilinear(align_corners)(emb [B][h][w][128] -> H x W),
-// [161..192) = 0;  act fp16 [B][H][W][32], rel fp32 [B][H][W]
+// ConditionalLogBinomial input: A[pix][0..128) = bilinear(align_corners)(emb [B][h][w][128] -> H x W), [128..160) = act, [160] = rel,
+// [161..192) = 0 (the packed weight uses the same channel order);  act fp16 [B][H][W][32], rel fp32 [B][H][W]
 int zoe_clb_concat(cudaStream_t st, const __half* act, const float* rel, const __half* emb, int B, int h, int w, int H, int W, __half* A);
 // g fp16 [pix][ldg >= 80] (GELU'd hidden) -> 4 outputs (w2 fp32 [4][80], b2 [4]) -> softplus -> p, temperature -> log-binomial
 // softmax over 64 bins -> sum_k prob_k * bilinear(align_corners)(bins [B][h][w][64] fp32)_k -> depth fp32 [B][H][W]

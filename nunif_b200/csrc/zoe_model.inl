@@ -157,7 +157,25 @@ static std::shared_ptr<ZoeW> pack_zoedepth(Packer& pk) {
         w.att2[i] = pack_conv(pk, "attractors." + s + "._net.2", w.n_att[i], 128, 1, 1, 0, /*cout_pad=*/16);
     }
     // ConditionalLogBinomial mlp: (32 + 1 + 128 = 161 -> K padded to 192) -> 80 (N padded to 96) -> GELU -> 4
-    w.clb1 = pack_conv(pk, "conditional_log_binomial.mlp.0", 80, 161, 1, 1, /*cin_pad=*/192, /*cout_pad=*/96);
+    // input channels are re-ordered [embedding 128 | activation 32 | relative depth | 31 zeros] so that zoe_clb_concat moves
+    // whole 16-byte groups (the reference concatenates [activation | relative depth | embedding])
+    {
+        Lin l;
+        l.N = 96; l.K = 192;
+        const float* cw = pk.get("conditional_log_binomial.mlp.0.weight", (int64_t)80 * 161);
+        const float* cb = pk.get("conditional_log_binomial.mlp.0.bias", 80);
+        if (cw && cb) {
+            std::vector<float> wv((size_t)96 * 192, 0.f), bv(96, 0.f);
+            for (int n = 0; n < 80; ++n) {
+                for (int j = 0; j < 128; ++j) wv[(size_t)n * 192 + j] = cw[(size_t)n * 161 + 33 + j];
+                for (int j = 0; j < 33; ++j) wv[(size_t)n * 192 + 128 + j] = cw[(size_t)n * 161 + j];
+                bv[n] = cb[n];
+            }
+            l.w = pk.add_f16(wv);
+            l.b = pk.add_f32(bv);
+        }
+        w.clb1 = l;
+    }
     if (const float* c2 = pk.get("conditional_log_binomial.mlp.2.weight", 4 * 80)) {
         std::vector<float> v(c2, c2 + 320);
         for (auto& x : v) x = __half2float(__float2half_rn(x));   // the reference runs this conv in fp16
