@@ -141,6 +141,9 @@ int nb200_depth_anything_forward(nb200_model* m, const float* x, int B, int H, i
  * x [B][3][H][W] fp32, normalised (x - 0.5) / 0.5 and reflection padded (nb200_zoe_preprocess), H and W multiples of 32
  * -> depth [B][H][W] fp32 (metric depth, larger = farther; batch_infer negates it, zoedepth_model.py:124-130). */
 int nb200_zoedepth_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth, void* stream);
+/* Host-only helper of the same path: the per-block relative-position table ((2g-1)^2 + 3 rows x heads, learned on a g x g token
+ * grid) resampled for a ph x pw grid as MiDaS backbones/beit.py `_get_rel_pos_bias` does (bilinear, the 3 class-token rows kept). */
+int nb200_zoe_rel_pos_table(const float* table, int g, int heads, int ph, int pw, float* out);
 
 /* iw3.depth_aa (iw3/models/depth_aa.py:46-87; applied by batch_infer when depth_aa is set, iw3/depth_anything_model.py:153-154):
  * x [B][1][H][W] fp32 -> out, same shape.  mode 0 = forward in eval mode (clamp to [0,1]), 1 = infer (normalise by the

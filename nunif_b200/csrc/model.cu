@@ -828,6 +828,16 @@ extern "C" int nb200_debug_tap(int id, void* dev_buf, size_t capacity) {
     return 0;
 }
 
+// Host-only: the relative-position table resample of the BEiT blocks (MiDaS beit.py _get_rel_pos_bias) for a ph x pw token grid.
+// table [(2g-1)^2 + 3][heads] -> out [(2ph-1)(2pw-1) + 3][heads].  No GPU needed (tests/test_host_logic.py).
+extern "C" int nb200_zoe_rel_pos_table(const float* table, int g, int heads, int ph, int pw, float* out) {
+    NB_CHECK(table && out, "null pointer");
+    NB_CHECK(g > 0 && heads > 0 && ph > 0 && pw > 0, "bad shape");
+    const size_t n = ((size_t)(2 * g - 1) * (2 * g - 1) + 3) * heads;
+    zoe_resample_table(std::vector<float>(table, table + n), g, heads, ph, pw, out);
+    return 0;
+}
+
 // ZoeDepth.forward(x)['metric_depth'] (what zoedepth_model._forward calls, iw3/zoedepth_model.py:23-27)
 extern "C" int nb200_zoedepth_forward(nb200_model* m, const float* x, int B, int H, int W, float* depth, void* stream) {
     NB_CHECK(m && x && depth, "null pointer");

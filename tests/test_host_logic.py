@@ -86,3 +86,25 @@ def test_bench_launch_list_summary_agrees_with_live_shares():
     live = eval(out.split("class shares (bench):")[1].splitlines()[0].strip())
     for k in ("gemm", "window_attention"):
         assert abs(ncu[k] - live[k]) < 0.03, (k, ncu[k], live[k])
+
+
+@pytest.mark.parametrize("g,ph,pw", [(24, 24, 32), (24, 24, 44), (6, 4, 6), (6, 6, 6), (5, 9, 3)])
+def test_zoe_relative_position_table_resample_matches_oracle(g, ph, pw):
+    """Host logic of the ZoeD_N path (no GPU): the BEiT relative-position table resampled for a non-training token grid
+    (csrc/zoe_model.inl zoe_resample_table) against the oracle's F.interpolate restatement of MiDaS `_get_rel_pos_bias`."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from nunif_b200 import _lib
+    heads = 4
+    S = 2 * g - 1
+    tab = torch.randn(S * S + 3, heads, generator=torch.Generator().manual_seed(g * 100 + ph * 10 + pw))
+    nh, nw = 2 * ph - 1, 2 * pw - 1
+    out = torch.empty(nh * nw + 3, heads)
+    _lib.check(_lib.lib().nb200_zoe_rel_pos_table(ctypes.c_void_p(tab.data_ptr()), g, heads, ph, pw, ctypes.c_void_p(out.data_ptr())))
+    sub = tab[:S * S].reshape(1, S, S, heads).permute(0, 3, 1, 2)
+    want = F.interpolate(sub, size=(nh, nw), mode="bilinear").permute(0, 2, 3, 1).reshape(nh * nw, heads)
+    want = torch.cat([want, tab[S * S:]])
+    assert float((out - want).abs().max()) < 2e-6
+    if (ph, pw) == (g, g):
+        assert torch.equal(out, tab)
