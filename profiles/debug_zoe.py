@@ -25,6 +25,7 @@ t0 = time.time()
 net = ZoeDepthNet(sd, dev)
 print(f"pack + upload: {time.time() - t0:.1f} s")
 sdc = {k: v.to(dev) for k, v in sd.items()}
+torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False   # a true fp32 reference
 with torch.no_grad():
     ref = oz.zoedepth_forward(sdc, x.to(dev), cfg_o, return_all=True)
     with torch.autocast("cuda", dtype=torch.float16):

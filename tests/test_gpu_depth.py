@@ -6,7 +6,7 @@ error against the fp32 oracle is compared with the error of the oracle itself ru
 import pytest
 import torch
 
-from tests.util import log_metric, stats
+from tests.util import log_metric, stats, true_fp32
 from nunif_b200 import synth
 from oracle import depth_anything as oda
 
@@ -17,7 +17,8 @@ DEV = "cuda:0"
 def _refs(sd, x):
     sdc = {k: v.to(DEV) for k, v in sd.items()}
     with torch.no_grad():
-        ref32 = oda.depth_anything_forward(sdc, x.to(DEV).float())
+        with true_fp32():
+            ref32 = oda.depth_anything_forward(sdc, x.to(DEV).float())
         with torch.autocast("cuda", dtype=torch.float16):
             refamp = oda.depth_anything_forward(sdc, x.to(DEV)).float()
     return ref32.cpu(), refamp.cpu()

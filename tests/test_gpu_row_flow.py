@@ -81,9 +81,8 @@ def test_row_flow_1080p_runs_and_matches_oracle_amp():
     l, r = apply_divergence_nn_LR(m, c, d, 2.0, 0.5)
     # the fp32 oracle evaluated on the GPU by torch (a 1080p frame through it takes minutes on the CPU)
     sdc = {k: v.to(DEV) for k, v in sd.items()}
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
-    with torch.no_grad():
+    from tests.util import true_fp32
+    with torch.no_grad(), true_fp32():
         lo, ro = _oracle_lr_on_device(sdc, c, d, 2.0, 0.5)
     sl, sr = stats(l, lo), stats(r, ro)
     log_metric("row_flow_1080p", left_max=sl["max"], right_max=sr["max"], left_mean=sl["mean"], right_mean=sr["mean"])

