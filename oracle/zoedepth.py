@@ -174,7 +174,7 @@ def log_binom(n, k, eps=1e-7):
     return n * torch.log(n) - k * torch.log(k) - (n - k) * torch.log(n - k + eps)
 
 
-def metric_head(sd, act, bottleneck, blocks, rel):
+def metric_head(sd, act, bottleneck, blocks, rel, internals=None):
     x = F.conv2d(bottleneck, sd["conv2.weight"], sd["conv2.bias"])
     prev_bin = _mlp2(sd, "seed_bin_regressor.", x, F.softplus).float()        # SeedBinRegressorUnnormed
     prev_emb = _mlp2(sd, "seed_projector.", x)
@@ -190,6 +190,8 @@ def metric_head(sd, act, bottleneck, blocks, rel):
         delta = delta / N_ATTRACTORS[i]                                        # attractor_kind "mean"
         prev_bin = c + delta
         prev_emb = emb
+        if internals is not None:
+            internals.setdefault("bins", []).append(prev_bin)
     last = torch.cat([act, F.interpolate(rel.unsqueeze(1), size=act.shape[2:], mode="bilinear", align_corners=True).to(act.dtype)], dim=1)
     emb = F.interpolate(prev_emb, last.shape[-2:], mode="bilinear", align_corners=True)
     # ConditionalLogBinomial (bottleneck_factor 2, p_eps 1e-4, act softmax)
@@ -200,6 +202,8 @@ def metric_head(sd, act, bottleneck, blocks, rel):
     tmp = pt[:, 2:] + 1e-4
     tmp = (tmp[:, 0] / (tmp[:, 0] + tmp[:, 1])).unsqueeze(1)
     tmp = (MAX_TEMP - MIN_TEMP) * tmp + MIN_TEMP
+    if internals is not None:
+        internals["p"], internals["temperature"] = p, tmp
     p = p.unsqueeze(1)
     k = torch.arange(0, N_BINS, device=p.device, dtype=torch.float32).view(1, -1, 1, 1)
     km1 = torch.tensor([N_BINS - 1], device=p.device, dtype=torch.float32).view(1, -1, 1, 1)
@@ -220,9 +224,10 @@ def zoedepth_forward(sd, x, cfg=ZOED_N, return_all=False):
     feats = beit_features(sd, x, cfg)
     blocks, bottleneck = dpt_neck(sd, feats, ph, pw, cfg)
     rel, act = relative_head(sd, blocks[-1])
-    out = metric_head(sd, act, bottleneck, blocks, rel)
+    internals = {} if return_all else None
+    out = metric_head(sd, act, bottleneck, blocks, rel, internals)
     if return_all:
-        return {"feats": feats, "blocks": blocks, "bottleneck": bottleneck, "rel": rel, "act": act, "metric_depth": out}
+        return {"feats": feats, "blocks": blocks, "bottleneck": bottleneck, "rel": rel, "act": act, "metric_depth": out, **internals}
     return out
 
 

@@ -46,6 +46,8 @@ for i in range(4):
 stages.append((8, "bottleneck", nhwc(ref["bottleneck"]), nhwc(amp["bottleneck"]), torch.float16))
 stages.append((9, "out_conv act", nhwc(ref["act"]), nhwc(amp["act"]), torch.float16))
 stages.append((10, "relative depth", ref["rel"], amp["rel"], torch.float32))
+for i in range(4):
+    stages.append((11 + i, f"bins level {i}", nhwc(ref["bins"][i]), nhwc(amp["bins"][i]), torch.float32))
 buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 lib = _lib.lib()
 
@@ -71,6 +73,20 @@ _lib.check(lib.nb200_debug_tap(-1, None, 0))
 out = net(xd)
 torch.cuda.synchronize()
 report("metric depth", out, ref["metric_depth"], amp["metric_depth"])
+e = (out.float().cpu() - ref["metric_depth"].float().cpu()).abs()
+flat = e.flatten().topk(5)
+for v, idx in zip(flat.values.tolist(), flat.indices.tolist()):
+    b, r = divmod(idx, H * W)
+    yy, xx = divmod(r, W)
+    print(f"  worst pixel b={b} y={yy} x={xx}: ours {float(out[b, 0, yy, xx]):.5f} fp32 {float(ref['metric_depth'][b, 0, yy, xx]):.5f} amp "
+          f"{float(amp['metric_depth'][b, 0, yy, xx]):.5f} | p fp32 {float(ref['p'][b, yy, xx]):.6f} amp {float(amp['p'][b, yy, xx]):.6f} | "
+          f"T fp32 {float(ref['temperature'][b, 0, yy, xx]):.5f} amp {float(amp['temperature'][b, 0, yy, xx]):.5f}")
+ea = (amp["metric_depth"].float().cpu() - ref["metric_depth"].float().cpu()).abs()
+flat = ea.flatten().topk(3)
+for v, idx in zip(flat.values.tolist(), flat.indices.tolist()):
+    b, r = divmod(idx, H * W)
+    yy, xx = divmod(r, W)
+    print(f"  worst AMP pixel b={b} y={yy} x={xx}: err {v:.5f} T fp32 {float(ref['temperature'][b, 0, yy, xx]):.5f}")
 # timing
 for _ in range(2):
     net(xd)
