@@ -395,9 +395,35 @@ def gen_mlbw_variants():
     save("mlbw_variants", **out)
 
 
+def gen_zoedepth_infer():
+    """The REAL iw3/zoedepth_model.py batch_infer (:89-148: batch_preprocess, flip TTA, crop of the reflection pad, dilation in
+    negative space, negation) around a stand-in network: the third-party ZoeD_N module is replaced by the oracle's restatement
+    (oracle/zoedepth.py, reduced widths) exposed through the same `model(x)['metric_depth']` interface, so the golden pins the
+    reference's wrapper logic while the network itself stays pinned to transformers (test_oracle_golden)."""
+    from iw3.zoedepth_model import batch_infer as ref_batch_infer
+    from oracle import zoedepth as oz
+    sd = synth.zoedepth_state_dict(5, synth.ZOED_MINI)
+
+    class Stub:
+        device = torch.device("cpu")
+        prep_h_height, prep_v_height, prep_mod = 96, 128, 32
+
+        def __call__(self, x):
+            return {"metric_depth": oz.zoedepth_forward(sd, x, oz.ZOED_MINI)}
+
+    land = torch.stack([synth.synth_image(71 + i, 3, 180, 320, smooth=False) for i in range(2)])
+    port = synth.synth_image(73, 3, 240, 160, smooth=False)
+    out = {"land": land, "port": port}
+    for flip in (0, 1):
+        for dil in (0, 2):
+            out[f"land_f{flip}_d{dil}"] = ref_batch_infer(Stub(), land.clone(), flip_aug=bool(flip), enable_amp=False, edge_dilation=dil)
+            out[f"port_f{flip}_d{dil}"] = ref_batch_infer(Stub(), port.clone(), flip_aug=bool(flip), enable_amp=False, edge_dilation=dil)
+    save("zoedepth_infer", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "row_flow_steps", "postprocess", "depth_scaler", "depth_aa", "mlbw", "mlbw_variants"]
+    which = sys.argv[1:] or ["seam", "models", "iw3", "alpha_tta", "frames", "row_flow", "row_flow_steps", "postprocess", "depth_scaler", "depth_aa", "mlbw", "mlbw_variants", "zoedepth_infer"]
     if "seam" in which:
         gen_seam_config()
     if "models" in which:
@@ -422,3 +448,5 @@ if __name__ == "__main__":
         gen_mlbw()
     if "mlbw_variants" in which:
         gen_mlbw_variants()
+    if "zoedepth_infer" in which:
+        gen_zoedepth_infer()

@@ -133,3 +133,29 @@ def test_zoedepth_model_infer_pipeline_1080p():
         assert model.get_ema_buffer_size() >= 1
         dn = model.minmax_normalize_chw(model.infer(x[0].to(DEV), tta=False, edge_dilation=2))
         assert dn.shape == d.shape[1:] and float(dn.min()) >= 0.0 and float(dn.max()) <= 1.0
+
+
+def test_zoedepth_infer_matches_reference_batch_infer_golden():
+    """ZoeDepthModel.infer against the REAL iw3/zoedepth_model.batch_infer run on the CPU in fp32 around the oracle network
+    (tests/golden/zoedepth_infer.npz, oracle/gen_golden.py:gen_zoedepth_infer): landscape batch and a portrait single image (square
+    reflection pad), flip TTA on / off, edge dilation 0 / 2.  Bounds: the fp16 error level of the reduced network measured by
+    the tests above (mean 1e-4, p99.9 2e-3 of the range) with a safety factor; the exact criterion is in _check."""
+    from tests.util import load_golden, t
+    from nunif_b200.iw3 import ZoeDepthModel
+    g = load_golden("zoedepth_infer")
+    sd = synth.zoedepth_state_dict(5, synth.ZOED_MINI)
+    model = ZoeDepthModel("ZoeD_N").load_state_dict(sd, gpu=0)
+    model.model.prep_h_height, model.model.prep_v_height = 96, 128       # the sizes the golden was generated with
+    land, port = t(g["land"]).to(DEV), t(g["port"]).to(DEV)
+    with torch.inference_mode():
+        for flip in (0, 1):
+            for dil in (0, 2):
+                for name, x in (("land", land), ("port", port)):
+                    want = t(g[f"{name}_f{flip}_d{dil}"])
+                    got = model.infer(x, tta=bool(flip), edge_dilation=dil).cpu()
+                    assert got.shape == want.shape, (name, flip, dil, got.shape, want.shape)
+                    scale = float(want.abs().max())
+                    e = stats(got, want)
+                    log_metric(f"zoedepth_infer_golden_{name}_f{flip}_d{dil}", max=e["max"], mean=e["mean"], p999=e["p999"], scale=scale)
+                    assert torch.isfinite(got).all()
+                    assert e["mean"] <= 1e-3 * scale and e["p999"] <= 1e-2 * scale and e["max"] <= 0.1 * scale, (name, flip, dil, e, scale)

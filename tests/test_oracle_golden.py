@@ -501,3 +501,22 @@ def test_zoedepth_oracle_matches_transformers():
     assert got.shape == want.shape == (2, 64, 96)
     assert float(want.std()) > 0.05
     assert float((got - want).abs().max()) < 2e-4 * float(want.abs().max())
+
+
+def test_zoedepth_batch_infer_oracle_matches_reference():
+    """oracle/zoedepth.batch_infer against the REAL iw3/zoedepth_model.batch_infer (golden generated around a stand-in network,
+    oracle/gen_golden.py:gen_zoedepth_infer): preprocessing incl. the square-padded portrait case, flip TTA, pad crop,
+    dilation in negative space, negation, single-image squeeze."""
+    from oracle import zoedepth as oz
+    g = load_golden("zoedepth_infer")
+    sd = synth.zoedepth_state_dict(5, synth.ZOED_MINI)
+    with torch.no_grad():
+        for flip in (0, 1):
+            for dil in (0, 2):
+                got = oz.batch_infer(sd, t(g["land"]), flip_aug=bool(flip), edge_dilation=dil, h_height=96, v_height=128, cfg=oz.ZOED_MINI)
+                want = t(g[f"land_f{flip}_d{dil}"])
+                assert got.shape == want.shape and float((got - want).abs().max()) < 2e-4 * float(want.abs().max()), (flip, dil)
+                got = oz.batch_infer(sd, t(g["port"]).unsqueeze(0), flip_aug=bool(flip), edge_dilation=dil, h_height=96, v_height=128,
+                                     cfg=oz.ZOED_MINI)[0]
+                want = t(g[f"port_f{flip}_d{dil}"])
+                assert got.shape == want.shape and float((got - want).abs().max()) < 2e-4 * float(want.abs().max()), (flip, dil)
