@@ -108,3 +108,33 @@ def test_zoe_relative_position_table_resample_matches_oracle(g, ph, pw):
     assert float((out - want).abs().max()) < 2e-6
     if (ph, pw) == (g, g):
         assert torch.equal(out, tab)
+
+
+def test_zoedepth_model_host_contract():
+    """ZoeDepthModel host-side contract (iw3/zoedepth_model.py:151-233) without a GPU: supported types, checkpoint path,
+    metric flag, loud errors for the checkpoints the engine does not implement, checkpoint dict unwrapping."""
+    import torch
+    from nunif_b200.iw3 import ZoeDepthModel
+    from nunif_b200.iw3 import zoedepth_model as zm
+    assert ZoeDepthModel.supported("ZoeD_N") and not ZoeDepthModel.supported("ZoeD_K") and not ZoeDepthModel.supported("ZoeD_Any_N")
+    assert ZoeDepthModel.get_name() == "ZoeDepth"
+    assert ZoeDepthModel.get_model_path("ZoeD_N").endswith(os.path.join("checkpoints", "ZoeD_M12_N.pt"))
+    m = ZoeDepthModel("ZoeD_N")
+    assert m.is_metric() and not m.loaded()
+    for bad in ("ZoeD_K", "ZoeD_NK", "ZoeD_Any_K", "Any_V2_S"):
+        with pytest.raises(ValueError):
+            ZoeDepthModel(bad)
+    with pytest.raises(FileNotFoundError):
+        m.load_model("ZoeD_N", device=torch.device("cuda", 0))        # no checkpoint on disk, never downloads
+    sd = {"a": torch.zeros(1)}
+    assert zm._strip_checkpoint({"model": sd, "epoch": 3}) is sd and zm._strip_checkpoint(sd) is sd
+    with pytest.raises(RuntimeError):
+        zm.ZoeDepthNet(sd, "cpu")                                      # no CPU path
+
+
+def test_iw3_workloads_are_declared_for_both_bench_arms():
+    import bench
+    for key, wl in bench.IW3_WORKLOADS.items():
+        assert wl["frame"] in bench.FRAME and wl["batch"] > 0 and wl["depth"] in ("Any_V2_S", "ZoeD_N")
+        assert wl["method"] in ("forward_fill", "backward")
+    assert "iw3_4k_zoe" in bench.IW3_WORKLOADS and "swin4x_4k" in bench.WORKLOADS
