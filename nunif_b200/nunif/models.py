@@ -124,9 +124,35 @@ class B200I2IModel:
         return z
 
 
+NOT_BUILT = {   # registered by the reference (waifu2x/models/swin_unet.py:306-336,390-394) but outside this engine: loud, not "unknown"
+    "waifu2x.swin_unet_8x": "SwinUNet8x (scale_factor 8 variant, no released weights)",
+    "waifu2x.swin_unet_4xl": "swin_unet_4xl (base_dim 192 + LayerNormNoBias variant, no released weights)",
+}
+
+
 def create_model(name, state_dict, device="cuda:0", **kwargs):
-    """nunif.models.create_model + load_state_dict (register.py:52-63, utils.py:57-58)."""
-    return B200I2IModel(name, state_dict, device=device, no_clip=bool(kwargs.get("no_clip", False)))
+    """nunif.models.create_model + load_state_dict (register.py:52-63, utils.py:57-58).  ``kwargs`` are the constructor
+    arguments a checkpoint carries (`load_model` passes `data["kwargs"]`): the ones that change the arithmetic and are not
+    built raise instead of being ignored."""
+    if name in NOT_BUILT:
+        raise NotImplementedError(f"{name}: {NOT_BUILT[name]} is not implemented by nunif_b200")
+    if kwargs.get("pre_antialias"):
+        raise NotImplementedError("pre_antialias=True (swin_unet.py:252-258,281-282: bicubic x2 up / down of every tile before the "
+                                  "network) is not implemented by nunif_b200")
+    if kwargs.get("layer_norm") or kwargs.get("base_dim", 96) != 96:
+        raise NotImplementedError("swin_unet variants with layer_norm=True / base_dim != 96 are not implemented by nunif_b200")
+    for k in ("in_channels", "out_channels"):
+        if kwargs.get(k, 3) != 3:
+            raise NotImplementedError(f"{k}={kwargs[k]}: the engine implements the released 3-channel models")
+    no_clip = bool(kwargs.get("no_clip", False))
+    if name == "waifu2x.swin_unet_downscaled":
+        # SwinUNetDownscaled (swin_unet.py:339-387): the 4x network (same `unet.*` keys) + antialiased bicubic /2 or /4
+        f = int(kwargs.get("downscale_factor", 2))
+        if f not in (2, 4):
+            raise AssertionError("downscale_factor must be 2 or 4")                      # :344
+        base = B200I2IModel("waifu2x.swin_unet_4x", state_dict, device=device, no_clip=no_clip)
+        return base.to_2x() if f == 2 else base.to_1x()
+    return B200I2IModel(name, state_dict, device=device, no_clip=no_clip)
 
 
 def load_model(model_path, device="cuda:0", weights_only=True):

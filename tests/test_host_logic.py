@@ -138,3 +138,26 @@ def test_iw3_workloads_are_declared_for_both_bench_arms():
         assert wl["frame"] in bench.FRAME and wl["batch"] > 0 and wl["depth"] in ("Any_V2_S", "ZoeD_N")
         assert wl["method"] in ("forward_fill", "backward")
     assert "iw3_4k_zoe" in bench.IW3_WORKLOADS and "swin4x_4k" in bench.WORKLOADS
+
+
+def test_create_model_refuses_unbuilt_variants_loudly():
+    """Constructor arguments that change the arithmetic are never ignored (no silent no-ops); all of these raise
+    before any CUDA call."""
+    import torch
+    from nunif_b200.nunif.models import create_model
+    sd = {"x": torch.zeros(1)}
+    for name in ("waifu2x.swin_unet_8x", "waifu2x.swin_unet_4xl"):
+        with pytest.raises(NotImplementedError):
+            create_model(name, sd, "cuda:0")
+    with pytest.raises(NotImplementedError, match="pre_antialias"):
+        create_model("waifu2x.swin_unet_4x", sd, "cuda:0", pre_antialias=True)
+    with pytest.raises(NotImplementedError):
+        create_model("waifu2x.swin_unet_4x", sd, "cuda:0", base_dim=192, layer_norm=True)
+    with pytest.raises(NotImplementedError):
+        create_model("waifu2x.upcunet", sd, "cuda:0", in_channels=1)
+    with pytest.raises(AssertionError):
+        create_model("waifu2x.swin_unet_downscaled", sd, "cuda:0", downscale_factor=3)
+    with pytest.raises(ValueError, match="Unknown model name"):
+        create_model("waifu2x.no_such_model", sd, "cuda:0")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        create_model("waifu2x.swin_unet_downscaled", sd, "cpu", downscale_factor=2)      # name accepted; the engine needs CUDA
